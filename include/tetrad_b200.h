@@ -1,0 +1,136 @@
+/*
+ * tetrad_b200 -- C ABI of the B200-native quartet-resolution hot path.
+ *
+ * This is the drop-in boundary for ONE path of eaton-lab/tetrad: the per-quartet loop
+ *   sample one SNP per locus -> 3 x (16x16) site-pattern counts -> SVDquartets score -> best split
+ * i.e. reference `new_infer_resolved_quartets` (tetrad/src/resolve_quartets.py:191-265) with its
+ * two numba kernels (`subsample_chunk_to_matrices` :42-73, `full_chunk_to_matrices` :76-104) and its
+ * numpy.linalg svd / matrix_rank calls (:242-243).  The reference has no FFI of its own (it is pure
+ * Python); INTEGRATION.md shows the ctypes stub a maintainer adds to route that function here.
+ *
+ * Conventions
+ *   - plain C, no exceptions; every call returns 0 on success or a negative TQ_E* code and
+ *     records a message retrievable with tq_last_error() (thread-local).
+ *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. torch tensors); pointers
+ *     named h_* are HOST pointers.  `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream).  Device-buffer calls only enqueue work: no hidden synchronisation.
+ *   - codes in tmparr: 0,1,2,3 = A,C,G,T; anything else is missing (the reference writes 78 = 'N').
+ *   - a quartet is four ascending tip indices; split k of the result means
+ *       0: t0 t1 | t2 t3     1: t0 t2 | t1 t3     2: t0 t3 | t1 t2
+ *     (reference tetrad/src/run_inference.py:41-45).
+ */
+#ifndef TETRAD_B200_H
+#define TETRAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQ_VERSION 100          /* 0.1.0 */
+
+#define TQ_OK            0
+#define TQ_EINVAL       -1      /* bad argument (NULL pointer, negative size, tip index >= ntips) */
+#define TQ_ELOCUS       -2      /* locus ids do not form one contiguous run per id */
+#define TQ_ECUDA        -3      /* a CUDA runtime call failed; see tq_last_error() */
+#define TQ_ENOMEM       -4
+
+int         tq_version(void);
+const char *tq_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Locus plan: the per-replicate locus structure shared by every quartet.
+ *
+ * Replaces the role of `tmpmap[:, 0]` inside subsample_chunk_to_matrices
+ * (resolve_quartets.py:58-64): the `last_loc` state machine keeps the first usable column of
+ * every run of equal locus id.  The plan sorts the locus runs by length (longest first), cuts
+ * them into tiles of 1024 loci and records, per tile, how many within-locus ranks it has; the
+ * packed matrix then stores "rank k of locus l" at bit l of plane k, so "first usable column
+ * of a locus" becomes "lowest k with the bit set" -- a running OR, with no cross-word scan.
+ *
+ * h_locus: tmpmap[:,0] on the host, `stride` = element stride (2 for the reference's u32[S,2]).
+ * Fails with TQ_ELOCUS when an id occurs in two separate runs (the reference's result would
+ * then depend on which columns are missing in between; its own get_spans assumes sorted ids).
+ * The plan uploads its small tables to `device` on `stream` and owns them.  device = -1 builds
+ * a host-only plan (layout queries via tq_plan_info / tq_plan_tables; no kernels can use it).
+ */
+typedef struct tq_plan tq_plan;
+
+int  tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride,
+                    int device, void *stream, tq_plan **out);
+void tq_plan_destroy(tq_plan *plan);
+
+/* info[0]=ncols  [1]=nloci  [2]=ntiles  [3]=row_words (u32 words per tip row of the packed matrix)
+ * info[4]=max locus length  [5]=padded columns (sum over tiles of ranks*1024)  [6]=device  [7]=0 */
+int  tq_plan_info(const tq_plan *plan, int64_t info[8]);
+
+/* Copies of the plan's tables (any pointer may be NULL): tile_off u32[ntiles+1] (offset of each
+ * tile inside a tip row, in 16-byte units), tile_k u32[ntiles] (ranks per tile), loc_start /
+ * loc_len u32[ntiles*1024] (first column and length of each locus in sorted order, 0-padded). */
+int  tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k,
+                    uint32_t *loc_start, uint32_t *loc_len);
+
+/* ------------------------------------------------------------------------------------------
+ * K1: pack.  d_tmparr u8[ntips][row_stride] (device)  ->  d_planes u32[ntips][row_words] (device):
+ * one-hot A/C/G/T bit-planes (missing = no bit set), interleaved as uint4 {A,C,G,T} per 32 loci.
+ * Replaces the row gather + `seqs >= 78` pass of resolve_quartets.py:212-216 (done once per
+ * replicate instead of once per quartet).  d_planes must be 16-byte aligned.
+ */
+int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t row_stride,
+            uint32_t *d_planes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3+K4: resolve.  For each of the m quartets in d_quartets u32[m][4]:
+ *   counts (resolve_quartets.py:42-104), singular values + ranks (:242-243), minrank (:246),
+ *   tail scores (:248), first argmin (:251), nsnps (:226,:264); zero-SNP quartets get scores
+ *   0.001 (:232) and a split drawn from a counter-based hash of (seed, tip ids) in place of the
+ *   reference's unseeded np.random.randint(3) (:231).
+ * Outputs (device): d_rscor f64[m][3], d_rstat u32[m][2] = (best split, nsnps),
+ *   d_counts u32[m][256] or NULL = mats[0] row-major (index 64a+16b+4c+d),
+ *   d_minrank u32[m] or NULL.
+ * subsample != 0 -> one SNP per locus (subsample_chunk_to_matrices); 0 -> all SNPs
+ * (full_chunk_to_matrices).  Tip indices must be < ntips (checked on the device: offending
+ * quartets get best = 0xFFFFFFFF and the call's status word, if given, is set non-zero).
+ */
+int tq_resolve(const tq_plan *plan, const uint32_t *d_planes, int64_t ntips,
+               const uint32_t *d_quartets, int64_t m, int subsample, uint64_t seed,
+               double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts, uint32_t *d_minrank,
+               uint32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer entry: the whole of new_infer_resolved_quartets(tmparr, tmpmap, quartets,
+ * subsample_snps) for numpy callers.  Copies inputs to the device, plans, packs, resolves,
+ * copies results back and synchronises.  `ctx` keeps device/pinned staging buffers between
+ * calls (the reference re-reads tmparr per chunk, resolve_quartets.py:33-35; with a ctx the
+ * packed matrix is reused when the same tmparr/tmpmap pointers+sizes+`epoch` come again).
+ */
+typedef struct tq_ctx tq_ctx;
+
+int  tq_ctx_create(int device, tq_ctx **out);
+void tq_ctx_destroy(tq_ctx *ctx);
+
+int tq_resolve_host(tq_ctx *ctx,
+                    const uint8_t *h_tmparr, int64_t ntips, int64_t ncols, int64_t row_stride,
+                    const uint32_t *h_locus, int64_t locus_stride,
+                    const uint32_t *h_quartets, int64_t m, int subsample, uint64_t seed,
+                    uint64_t epoch,
+                    double *h_rscor, uint32_t *h_rstat, uint32_t *h_counts, uint32_t *h_minrank);
+
+/* bytes copied by the last tq_resolve_host call on this ctx: out[0]=host->device, out[1]=device->host */
+int tq_ctx_last_traffic(const tq_ctx *ctx, int64_t out[2]);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py): pipe micro-benchmarks on `device`.
+ * kind 0: POPC  (result: popc32 thread-instructions per second)
+ * kind 1: LOP3  (and/or)      kind 2: DFMA        kind 3: device copy (bytes/s, read+write)
+ */
+int tq_microbench(int device, int kind, double *result);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t tq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETRAD_B200_H */

@@ -1,0 +1,170 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the golden vectors of the
+executed reference and against the oracle on seeded inputs.  Nothing here reads /root/reference."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, assert_best_matches, assert_scores_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import tetrad_b200
+    return tetrad_b200
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("mode", ["sub", "full"])
+def test_golden_host_entry(tb, case, mode):
+    """new_infer_resolved_quartets (tq_resolve_host) == reference outputs."""
+    g = load_golden(case)
+    sub = mode == "sub"
+    q, rstat, rscor, extra = tb.new_infer_resolved_quartets(
+        g["tmparr"], g["tmpmap"], g["quartets"], sub, return_counts=True)
+    assert (q == g["quartets"]).all()
+    assert (extra["counts"] == g[f"{mode}_mats0"]).all(), "counts not bit-exact"
+    ref_stat, ref_scor = g[f"{mode}_rstat"], g[f"{mode}_rscor"]
+    assert (rstat[:, 1] == ref_stat[:, 1]).all()
+    assert_scores_close(rscor, ref_scor, ref_stat[:, 1])
+    assert_best_matches(rstat[:, 0], ref_scor, ref_stat)
+    has = ref_stat[:, 1] > 0
+    ref_minrank = np.minimum(10, g[f"{mode}_ranks"].min(axis=1))
+    assert (extra["minrank"][has] == ref_minrank[has]).all(), "minrank (matrix_rank) mismatch"
+
+
+@pytest.mark.parametrize("case", ["noisy12", "boot12"])
+def test_golden_device_engine(tb, case):
+    """QuartetResolver (tq_plan_create + tq_pack + tq_resolve on torch memory)."""
+    g = load_golden(case)
+    eng = tb.QuartetResolver(device=0)
+    eng.load(g["tmparr"], g["tmpmap"])
+    for mode, sub in (("sub", True), ("full", False)):
+        rstat, rscor, counts, minrank = eng.resolve(g["quartets"], sub, want_counts=True)
+        eng.check_status()
+        assert (counts.cpu().numpy().view(np.uint32).reshape(-1, 16, 16) == g[f"{mode}_mats0"]).all()
+        ref_stat, ref_scor = g[f"{mode}_rstat"], g[f"{mode}_rscor"]
+        assert_scores_close(rscor.cpu().numpy(), ref_scor, ref_stat[:, 1])
+        assert_best_matches(rstat[:, 0].cpu().numpy(), ref_scor, ref_stat)
+    eng.close()
+
+
+def test_zero_snp_quartets(tb, oracle):
+    g = load_golden("missing7")
+    for seed in (0, 5):
+        _, rstat, rscor = tb.new_infer_resolved_quartets(g["tmparr"], g["tmpmap"], g["quartets"], True, seed=seed)
+        _, ostat, oscor = oracle.new_infer_resolved_quartets(g["tmparr"], g["tmpmap"], g["quartets"], True, seed=seed)
+        zero = ostat[:, 1] == 0
+        assert zero.any() and (rscor[zero] == 0.001).all()
+        assert (rstat[zero] == ostat[zero]).all()          # same counter-based draw as the oracle
+
+
+@pytest.mark.parametrize("shape", [(9, 300, 1100), (16, 2500, 9000), (6, 2, 5), (5, 40, 40)])
+@pytest.mark.parametrize("sub", [True, False])
+def test_seeded_vs_oracle(tb, oracle, shape, sub):
+    from itertools import combinations
+    from tetrad_b200 import synth
+    n, nloci, nsnps = shape
+    d = synth.generate(n, nloci, nsnps, seed=100 + n)
+    db = synth.prepare_database(d.snps, d.snpsmap, seed=n)
+    quartets = np.array(list(combinations(range(n), 4)), dtype=np.uint32)
+    if len(quartets) > 400:
+        quartets = quartets[np.random.default_rng(1).choice(len(quartets), 400, replace=False)]
+    _, rstat, rscor, extra = tb.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], quartets, sub, return_counts=True)
+    _, ostat, oscor, det = oracle.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], quartets, sub, return_details=True)
+    assert (extra["counts"] == det["mats"][:, 0]).all()
+    assert (rstat[:, 1] == ostat[:, 1]).all()
+    assert_scores_close(rscor, oscor, ostat[:, 1])
+    assert_best_matches(rstat[:, 0], oscor, ostat)
+    has = ostat[:, 1] > 0
+    assert (extra["minrank"][has] == det["minrank"][has]).all()
+
+
+def test_bootstrap_replicate_vs_oracle(tb, oracle):
+    from tetrad_b200 import synth
+    d = synth.generate(10, 1500, 6000, seed=77)
+    db = synth.prepare_database(d.snps, d.snpsmap, seed=3)
+    rng = np.random.default_rng(9)
+    tmparr, tmpmap = synth.bootstrap_resample(db["seqarr"], db["spans"], rng)
+    quartets = np.array([[0, 1, 2, 3], [0, 4, 7, 9], [2, 3, 5, 8], [1, 5, 6, 9]], dtype=np.uint32)
+    _, rstat, rscor, extra = tb.new_infer_resolved_quartets(tmparr, tmpmap, quartets, True, return_counts=True)
+    _, ostat, oscor, det = oracle.new_infer_resolved_quartets(tmparr, tmpmap, quartets, True, return_details=True)
+    assert (extra["counts"] == det["mats"][:, 0]).all()
+    assert_scores_close(rscor, oscor, ostat[:, 1])
+
+
+def test_edge_cases(tb):
+    g = load_golden("tiny8")
+    # empty quartet list
+    q, rstat, rscor = tb.new_infer_resolved_quartets(g["tmparr"], g["tmpmap"], np.zeros((0, 4), np.uint32), True)
+    assert rstat.shape == (0, 2) and rscor.shape == (0, 3)
+    # tip index out of range is an error, not a crash
+    from tetrad_b200._lib import TetradB200Error
+    with pytest.raises(TetradB200Error):
+        tb.new_infer_resolved_quartets(g["tmparr"], g["tmpmap"], np.array([[0, 1, 2, 99]], np.uint32), True)
+    # locus ids split in two runs
+    bad = g["tmpmap"].copy()
+    bad[-1, 0] = bad[0, 0]
+    with pytest.raises(TetradB200Error):
+        tb.new_infer_resolved_quartets(g["tmparr"], bad, g["quartets"][:2], True)
+    # unresolved byte (neither 0..3 nor >= 78) counts as missing
+    arr = g["tmparr"].copy()
+    arr[0, :] = 66
+    _, rstat, _ = tb.new_infer_resolved_quartets(arr, g["tmpmap"], np.array([[0, 1, 2, 3]], np.uint32), True)
+    assert rstat[0, 1] == 0
+    # device engine flags bad tips without crashing
+    eng = tb.QuartetResolver(device=0).load(g["tmparr"], g["tmpmap"])
+    eng.resolve(np.array([[0, 1, 2, 200]], np.uint32))
+    with pytest.raises(IndexError):
+        eng.check_status()
+
+
+def test_many_tiles_and_long_loci(tb, oracle):
+    """> 1 tile (1024 loci each), one very long locus, loci of length 1."""
+    rng = np.random.default_rng(4)
+    lens = np.concatenate([[70], rng.integers(1, 7, size=2600), np.ones(300, dtype=np.int64)])
+    rng.shuffle(lens)
+    locus = np.repeat(np.arange(lens.size), lens)
+    ncols = locus.size
+    tmparr = rng.integers(0, 4, size=(6, ncols)).astype(np.uint8)
+    tmparr[rng.random(tmparr.shape) < 0.15] = 78
+    tmpmap = np.stack([locus, np.arange(ncols)], 1).astype(np.uint32)
+    quartets = np.array([[0, 1, 2, 3], [1, 2, 4, 5], [0, 3, 4, 5]], dtype=np.uint32)
+    for sub in (True, False):
+        _, rstat, rscor, extra = tb.new_infer_resolved_quartets(tmparr, tmpmap, quartets, sub, return_counts=True)
+        _, ostat, oscor, det = oracle.new_infer_resolved_quartets(tmparr, tmpmap, quartets, sub, return_details=True)
+        assert (extra["counts"] == det["mats"][:, 0]).all()
+        assert_scores_close(rscor, oscor, ostat[:, 1])
+
+
+def test_size_independent_properties_at_bench_shape(tb):
+    """BASELINE config C2 shape (50 tips, 50k loci, 200k SNPs): properties that need no oracle."""
+    from tetrad_b200 import synth
+    db = synth.config_arrays("C2")
+    rng = np.random.default_rng(0)
+    quartets = np.sort(np.stack([rng.choice(50, 4, replace=False) for _ in range(3000)]), axis=1).astype(np.uint32)
+    eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+    rstat, rscor, counts, minrank = eng.resolve(quartets, True, want_counts=True)
+    frstat, frscor, fcounts, _ = eng.resolve(quartets, False, want_counts=True)
+    c = counts.cpu().numpy().view(np.uint32).astype(np.int64); fc = fcounts.cpu().numpy().view(np.uint32).astype(np.int64)
+    nloci = eng.info["nloci"]
+    assert (c.sum(1) == rstat[:, 1].cpu().numpy()).all() and (c.sum(1) <= nloci).all()
+    assert (fc >= c).all() and (fc.sum(1) <= 200_000).all()
+    for a in range(4):
+        assert (c[:, 85 * a] == 0).all() and (fc[:, 85 * a] == 0).all()
+    # relabelling tips permutes the count tensor: swap t0<->t1 and t2<->t3 => T[b,a,d,c]
+    perm = quartets[:, [1, 0, 3, 2]].copy()
+    _, _, pc, _ = eng.resolve(perm, True, want_counts=True)
+    t = c.reshape(-1, 4, 4, 4, 4)
+    assert (pc.cpu().numpy().view(np.uint32).reshape(-1, 4, 4, 4, 4) == t.transpose(0, 2, 1, 4, 3)).all()
+    # scores: finite, non-negative, Frobenius identity  sum_k sigma^2 = ||T||_F^2  bounds the tail
+    s = rscor.cpu().numpy()
+    assert np.isfinite(s).all() and (s >= 0).all()
+    assert (s.max(1) ** 2 <= (c.astype(np.float64) ** 2).sum(1) * (1 + 1e-12)).all()
+    # idempotence
+    rstat2, rscor2 = eng.resolve(quartets, True)
+    assert (rstat2 == rstat).all() and (rscor2 == rscor).all()

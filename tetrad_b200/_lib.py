@@ -1,0 +1,125 @@
+"""ctypes binding of ``libtetrad_b200.so`` (C ABI in ``include/tetrad_b200.h``).
+
+The shared library is built in-tree by ``build()`` (``nvcc`` for sm_100a) and there is no
+fallback of any kind: if it is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+_ROOT = _PKG.parent
+LIB_PATH = _PKG / "libtetrad_b200.so"
+SOURCES = [_PKG / "csrc" / "tq_kernels.cu", _PKG / "csrc" / "tq_api.cu"]
+HEADERS = [_PKG / "csrc" / "tq_kernels.cuh", _ROOT / "include" / "tetrad_b200.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+    "-Xlinker", "-rpath,/usr/local/cuda/lib64",
+]
+
+TQ_OK, TQ_EINVAL, TQ_ELOCUS, TQ_ECUDA, TQ_ENOMEM = 0, -1, -2, -3, -4
+
+_lib = None
+
+
+class TetradB200Error(RuntimeError):
+    """A libtetrad_b200 call failed (status code + tq_last_error text)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libtetrad_b200 error {code}: {message}")
+        self.code = code
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(exe).exists():
+        raise RuntimeError("nvcc not found; cannot build libtetrad_b200.so")
+    return exe
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    built = LIB_PATH.stat().st_mtime
+    return any(p.stat().st_mtime > built for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the CUDA sources for sm_100a into ``tetrad_b200/libtetrad_b200.so``."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, SOURCES)]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+def _declare(lib):
+    c = ctypes
+    vp, i64, u64, i32 = c.c_void_p, c.c_int64, c.c_uint64, c.c_int
+    lib.tq_version.restype = i32
+    lib.tq_version.argtypes = []
+    lib.tq_last_error.restype = c.c_char_p
+    lib.tq_last_error.argtypes = []
+    lib.tq_launch_count.restype = i64
+    lib.tq_launch_count.argtypes = []
+    lib.tq_plan_create.restype = i32
+    lib.tq_plan_create.argtypes = [vp, i64, i64, i32, vp, c.POINTER(vp)]
+    lib.tq_plan_destroy.restype = None
+    lib.tq_plan_destroy.argtypes = [vp]
+    lib.tq_plan_info.restype = i32
+    lib.tq_plan_info.argtypes = [vp, c.POINTER(i64)]
+    lib.tq_plan_tables.restype = i32
+    lib.tq_plan_tables.argtypes = [vp, vp, vp, vp, vp]
+    lib.tq_pack.restype = i32
+    lib.tq_pack.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.tq_resolve.restype = i32
+    lib.tq_resolve.argtypes = [vp, vp, i64, vp, i64, i32, u64, vp, vp, vp, vp, vp, vp]
+    lib.tq_ctx_create.restype = i32
+    lib.tq_ctx_create.argtypes = [i32, c.POINTER(vp)]
+    lib.tq_ctx_destroy.restype = None
+    lib.tq_ctx_destroy.argtypes = [vp]
+    lib.tq_resolve_host.restype = i32
+    lib.tq_resolve_host.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp, i64, i32, u64, u64, vp, vp, vp, vp]
+    lib.tq_ctx_last_traffic.restype = i32
+    lib.tq_ctx_last_traffic.argtypes = [vp, c.POINTER(i64)]
+    lib.tq_microbench.restype = i32
+    lib.tq_microbench.argtypes = [i32, i32, c.POINTER(c.c_double)]
+
+
+EXPORTS = [
+    "tq_version", "tq_last_error", "tq_launch_count", "tq_plan_create", "tq_plan_destroy",
+    "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
+    "tq_ctx_last_traffic", "tq_microbench",
+]
+
+
+def load():
+    """Load (never build) the shared library; raise if it is not there."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the CUDA extension is the only implementation; there is no CPU fallback)")
+        lib = ctypes.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else 0)
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != TQ_OK:
+        raise TetradB200Error(code, load().tq_last_error().decode("utf-8", "replace"))

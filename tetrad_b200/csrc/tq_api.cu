@@ -1,0 +1,384 @@
+// C ABI of libtetrad_b200.so (declared in include/tetrad_b200.h): locus plan, pack, resolve,
+// host-buffer convenience entry, micro-benchmarks.  Host code only; kernels are in tq_kernels.cu.
+#include "../../include/tetrad_b200.h"
+#include "tq_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define TQ_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(TQ_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct tq_plan {
+    int device = 0;
+    int num_sms = 0;
+    int64_t ncols = 0, nloci = 0, ntiles = 0, row_u4 = 0, max_len = 0, padded_cols = 0;
+    void *d_tables = nullptr;      // one allocation: tile_off | tile_k | loc_start | loc_len
+    std::vector<uint32_t> h_tables; // host copy of the same tables
+    size_t o_off = 0, o_k = 0, o_start = 0, o_len = 0;
+    tq::PlanDev dev{};
+};
+
+struct tq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // cached replicate state
+    tq_plan *plan = nullptr;
+    const void *key_arr = nullptr, *key_loc = nullptr;
+    int64_t key_ntips = -1, key_ncols = -1;
+    uint64_t key_epoch = 0;
+    // growable device buffers
+    void *d_tmparr = nullptr;  size_t cap_tmparr = 0;
+    void *d_planes = nullptr;  size_t cap_planes = 0;
+    void *d_quart = nullptr;   size_t cap_quart = 0;
+    void *d_out = nullptr;     size_t cap_out = 0;
+    void *h_pin = nullptr;     size_t cap_pin = 0;
+    int64_t last_h2d = 0, last_d2h = 0;
+};
+
+extern "C" {
+
+int tq_version(void) { return TQ_VERSION; }
+
+const char *tq_last_error(void) { return g_err; }
+
+int64_t tq_launch_count(void) { return tq::g_launches; }
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+int tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride, int device, void *stream,
+                   tq_plan **out)
+{
+    if (!out) return fail(TQ_EINVAL, "tq_plan_create: out is NULL");
+    *out = nullptr;
+    if (ncols < 0 || stride < 1 || (ncols > 0 && !h_locus))
+        return fail(TQ_EINVAL, "tq_plan_create: bad arguments (ncols=%lld stride=%lld)",
+                    (long long)ncols, (long long)stride);
+    if (ncols >= ((int64_t)1 << 32)) return fail(TQ_EINVAL, "tq_plan_create: ncols must be < 2^32");
+
+    // 1. locus runs (maximal runs of equal id, resolve_quartets.py:58-64)
+    std::vector<uint32_t> run_start, run_len;
+    bool monotone = true;
+    {
+        uint32_t prev = 0;
+        for (int64_t c = 0; c < ncols; ++c) {
+            const uint32_t id = h_locus[c * stride];
+            if (c == 0 || id != prev) {
+                if (c > 0 && id < prev) monotone = false;
+                run_start.push_back((uint32_t)c);
+                run_len.push_back(0);
+            }
+            run_len.back()++;
+            prev = id;
+        }
+    }
+    const int64_t nloci = (int64_t)run_start.size();
+    if (!monotone) {   // ids may come in any order, but every id must own exactly one run
+        std::unordered_set<uint32_t> seen;
+        seen.reserve((size_t)nloci * 2);
+        for (int64_t r = 0; r < nloci; ++r)
+            if (!seen.insert(h_locus[(int64_t)run_start[r] * stride]).second)
+                return fail(TQ_ELOCUS,
+                            "locus id %u occurs in more than one run of columns; sort tmpmap by locus",
+                            h_locus[(int64_t)run_start[r] * stride]);
+    }
+
+    // 2. stable counting sort of runs by length, longest first
+    uint32_t max_len = 0;
+    for (uint32_t l : run_len) max_len = std::max(max_len, l);
+    std::vector<int64_t> bucket((size_t)max_len + 2, 0);
+    for (uint32_t l : run_len) bucket[max_len - l + 1]++;
+    for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
+    const int64_t ntiles = (nloci + tq::kTileLoci - 1) / tq::kTileLoci;
+    const int64_t lpad = ntiles * tq::kTileLoci;
+    std::vector<uint32_t> tables;
+    // layout: tile_off[ntiles+1] | tile_k[ntiles] | loc_start[lpad] | loc_len[lpad]
+    const size_t o_off = 0, o_k = (size_t)ntiles + 1, o_start = o_k + (size_t)ntiles,
+                 o_len = o_start + (size_t)lpad, total = o_len + (size_t)lpad;
+    tables.assign(total + 4, 0u);
+    for (int64_t r = 0; r < nloci; ++r) {
+        const int64_t pos = bucket[max_len - run_len[r]]++;
+        tables[o_start + pos] = run_start[r];
+        tables[o_len + pos] = run_len[r];
+    }
+    int64_t off = 0, padded = 0;
+    for (int64_t t = 0; t < ntiles; ++t) {
+        const uint32_t k = tables[o_len + t * tq::kTileLoci];   // longest locus of the tile
+        tables[o_off + t] = (uint32_t)off;
+        tables[o_k + t] = k;
+        off += (int64_t)k * tq::kTileWords;
+        padded += (int64_t)k * tq::kTileLoci;
+        if (off >= ((int64_t)1 << 31)) return fail(TQ_EINVAL, "tq_plan_create: packed row too large");
+    }
+    tables[o_off + ntiles] = (uint32_t)off;
+
+    tq_plan *p = new (std::nothrow) tq_plan();
+    if (!p) return fail(TQ_ENOMEM, "tq_plan_create: out of host memory");
+    p->device = device;
+    p->ncols = ncols; p->nloci = nloci; p->ntiles = ntiles; p->row_u4 = off;
+    p->max_len = max_len; p->padded_cols = padded;
+    p->o_off = o_off; p->o_k = o_k; p->o_start = o_start; p->o_len = o_len;
+    p->dev.ntiles = (int)ntiles;
+    p->dev.row_u4 = (uint32_t)off;
+    if (device < 0) {               // host-only plan: layout queries, no kernels
+        p->h_tables.swap(tables);
+        *out = p;
+        return TQ_OK;
+    }
+
+    DeviceGuard guard(device);
+    cudaError_t e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_tables, (total + 4) * sizeof(uint32_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(p->d_tables, tables.data(), (total + 4) * sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    // `tables` is pageable: the async copy stages it before returning, so it may go out of scope
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        if (p->d_tables) cudaFree(p->d_tables);
+        delete p;
+        return fail(TQ_ECUDA, "tq_plan_create: %s", cudaGetErrorString(e));
+    }
+    const uint32_t *base = static_cast<const uint32_t *>(p->d_tables);
+    p->dev.tile_off = base + o_off;
+    p->dev.tile_k = base + o_k;
+    p->dev.loc_start = base + o_start;
+    p->dev.loc_len = base + o_len;
+    p->h_tables.swap(tables);
+    *out = p;
+    return TQ_OK;
+}
+
+int tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k, uint32_t *loc_start,
+                   uint32_t *loc_len)
+{
+    if (!plan) return fail(TQ_EINVAL, "tq_plan_tables: plan is NULL");
+    const uint32_t *t = plan->h_tables.data();
+    const size_t nt = (size_t)plan->ntiles, lp = nt * tq::kTileLoci;
+    if (tile_off) memcpy(tile_off, t + plan->o_off, (nt + 1) * sizeof(uint32_t));
+    if (tile_k) memcpy(tile_k, t + plan->o_k, nt * sizeof(uint32_t));
+    if (loc_start) memcpy(loc_start, t + plan->o_start, lp * sizeof(uint32_t));
+    if (loc_len) memcpy(loc_len, t + plan->o_len, lp * sizeof(uint32_t));
+    return TQ_OK;
+}
+
+void tq_plan_destroy(tq_plan *plan)
+{
+    if (!plan) return;
+    if (plan->d_tables) {
+        DeviceGuard guard(plan->device);
+        cudaFree(plan->d_tables);
+    }
+    delete plan;
+}
+
+int tq_plan_info(const tq_plan *plan, int64_t info[8])
+{
+    if (!plan || !info) return fail(TQ_EINVAL, "tq_plan_info: NULL argument");
+    info[0] = plan->ncols; info[1] = plan->nloci; info[2] = plan->ntiles;
+    info[3] = plan->row_u4 * 4; info[4] = plan->max_len; info[5] = plan->padded_cols;
+    info[6] = plan->device; info[7] = 0;
+    return TQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-buffer entries
+// ------------------------------------------------------------------------------------------
+int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t row_stride,
+            uint32_t *d_planes, void *stream)
+{
+    if (!plan) return fail(TQ_EINVAL, "tq_pack: plan is NULL");
+    if (plan->device < 0) return fail(TQ_EINVAL, "tq_pack: host-only plan (device < 0)");
+    if (ntips < 0 || ntips > 65535) return fail(TQ_EINVAL, "tq_pack: ntips=%lld out of range", (long long)ntips);
+    if (ntips == 0 || plan->row_u4 == 0) return TQ_OK;
+    if (!d_tmparr || !d_planes) return fail(TQ_EINVAL, "tq_pack: NULL device pointer");
+    if (row_stride < plan->ncols) return fail(TQ_EINVAL, "tq_pack: row_stride < ncols");
+    if (((uintptr_t)d_planes & 15u) != 0) return fail(TQ_EINVAL, "tq_pack: d_planes must be 16-byte aligned");
+    DeviceGuard guard(plan->device);
+    TQ_CUDA(tq::launch_pack(plan->dev, d_tmparr, ntips, row_stride, d_planes, (cudaStream_t)stream));
+    return TQ_OK;
+}
+
+int tq_resolve(const tq_plan *plan, const uint32_t *d_planes, int64_t ntips,
+               const uint32_t *d_quartets, int64_t m, int subsample, uint64_t seed,
+               double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts, uint32_t *d_minrank,
+               uint32_t *d_status, void *stream)
+{
+    if (!plan) return fail(TQ_EINVAL, "tq_resolve: plan is NULL");
+    if (plan->device < 0) return fail(TQ_EINVAL, "tq_resolve: host-only plan (device < 0)");
+    if (m < 0 || ntips < 0) return fail(TQ_EINVAL, "tq_resolve: negative size");
+    if (m == 0) return TQ_OK;
+    if (!d_quartets || !d_rscor || !d_rstat) return fail(TQ_EINVAL, "tq_resolve: NULL device pointer");
+    if (plan->row_u4 > 0 && !d_planes) return fail(TQ_EINVAL, "tq_resolve: d_planes is NULL");
+    if (((uintptr_t)d_planes & 15u) || ((uintptr_t)d_quartets & 15u) || ((uintptr_t)d_rstat & 7u))
+        return fail(TQ_EINVAL, "tq_resolve: planes/quartets must be 16-byte and rstat 8-byte aligned");
+    DeviceGuard guard(plan->device);
+    TQ_CUDA(tq::launch_resolve(plan->dev, d_planes, ntips, d_quartets, m, subsample != 0, seed, d_rscor,
+                               d_rstat, d_counts, d_minrank, d_status, plan->num_sms,
+                               (cudaStream_t)stream));
+    return TQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry
+// ------------------------------------------------------------------------------------------
+int tq_ctx_create(int device, tq_ctx **out)
+{
+    if (!out) return fail(TQ_EINVAL, "tq_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    TQ_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(TQ_EINVAL, "tq_ctx_create: no CUDA device %d", device);
+    tq_ctx *c = new (std::nothrow) tq_ctx();
+    if (!c) return fail(TQ_ENOMEM, "tq_ctx_create: out of host memory");
+    c->device = device;
+    DeviceGuard guard(device);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(TQ_ECUDA, "tq_ctx_create: %s", cudaGetErrorString(e)); }
+    *out = c;
+    return TQ_OK;
+}
+
+void tq_ctx_destroy(tq_ctx *c)
+{
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    if (c->plan) tq_plan_destroy(c->plan);
+    cudaFree(c->d_tmparr); cudaFree(c->d_planes); cudaFree(c->d_quart); cudaFree(c->d_out);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int tq_ctx_last_traffic(const tq_ctx *ctx, int64_t out[2])
+{
+    if (!ctx || !out) return fail(TQ_EINVAL, "tq_ctx_last_traffic: NULL argument");
+    out[0] = ctx->last_h2d; out[1] = ctx->last_d2h;
+    return TQ_OK;
+}
+
+static int grow(void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return TQ_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *cap = 0;
+    const size_t want = need + need / 8 + 256;
+    TQ_CUDA(cudaMalloc(buf, want));
+    *cap = want;
+    return TQ_OK;
+}
+
+int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t ncols, int64_t row_stride,
+                    const uint32_t *h_locus, int64_t locus_stride, const uint32_t *h_quartets, int64_t m,
+                    int subsample, uint64_t seed, uint64_t epoch, double *h_rscor, uint32_t *h_rstat,
+                    uint32_t *h_counts, uint32_t *h_minrank)
+{
+    if (!c) return fail(TQ_EINVAL, "tq_resolve_host: ctx is NULL");
+    if (ntips < 0 || ncols < 0 || m < 0 || row_stride < ncols || locus_stride < 1)
+        return fail(TQ_EINVAL, "tq_resolve_host: bad sizes");
+    if (ntips > 65535) return fail(TQ_EINVAL, "tq_resolve_host: ntips=%lld > 65535", (long long)ntips);
+    if ((ncols > 0 && ntips > 0 && !h_tmparr) || (ncols > 0 && !h_locus))
+        return fail(TQ_EINVAL, "tq_resolve_host: NULL input");
+    if (m > 0 && (!h_quartets || !h_rscor || !h_rstat)) return fail(TQ_EINVAL, "tq_resolve_host: NULL quartets/outputs");
+    for (int64_t q = 0; q < m; ++q)
+        for (int i = 0; i < 4; ++i)
+            if ((int64_t)h_quartets[4 * q + i] >= ntips)
+                return fail(TQ_EINVAL, "tq_resolve_host: quartet %lld has tip index %u >= ntips %lld",
+                            (long long)q, h_quartets[4 * q + i], (long long)ntips);
+    c->last_h2d = c->last_d2h = 0;
+    if (m == 0) return TQ_OK;
+    DeviceGuard guard(c->device);
+    int rc;
+
+    // (re)build the replicate state unless the caller presents the same arrays again
+    const bool same = c->plan && c->key_arr == h_tmparr && c->key_loc == h_locus && c->key_ntips == ntips &&
+                      c->key_ncols == ncols && c->key_epoch == epoch && epoch != 0;
+    if (!same) {
+        if (c->plan) { tq_plan_destroy(c->plan); c->plan = nullptr; }
+        if ((rc = tq_plan_create(h_locus, ncols, locus_stride, c->device, c->stream, &c->plan)) != TQ_OK) return rc;
+        c->last_h2d += (int64_t)((2 * c->plan->ntiles + 1 + 2 * c->plan->ntiles * tq::kTileLoci) * 4);
+        const size_t arr_bytes = (size_t)ntips * (size_t)ncols;
+        if ((rc = grow(&c->d_tmparr, &c->cap_tmparr, arr_bytes + 16)) != TQ_OK) return rc;
+        if ((rc = grow(&c->d_planes, &c->cap_planes, (size_t)ntips * (size_t)c->plan->row_u4 * 16 + 16)) != TQ_OK) return rc;
+        if (arr_bytes) {
+            TQ_CUDA(cudaMemcpy2DAsync(c->d_tmparr, (size_t)ncols, h_tmparr, (size_t)row_stride, (size_t)ncols,
+                                      (size_t)ntips, cudaMemcpyHostToDevice, c->stream));
+            c->last_h2d += (int64_t)arr_bytes;
+        }
+        if ((rc = tq_pack(c->plan, (const uint8_t *)c->d_tmparr, ntips, ncols, (uint32_t *)c->d_planes, c->stream)) != TQ_OK)
+            return rc;
+        c->key_arr = h_tmparr; c->key_loc = h_locus; c->key_ntips = ntips; c->key_ncols = ncols;
+        c->key_epoch = epoch;
+    }
+
+    // outputs: rscor f64[m][3] | rstat u32[m][2] | minrank u32[m] | status u32[4] | counts u32[m][256]
+    const size_t o_scor = 0, o_stat = o_scor + (size_t)m * 24, o_mr = o_stat + (size_t)m * 8,
+                 o_status = o_mr + (((size_t)m * 4 + 15) & ~(size_t)15),
+                 o_counts = o_status + 16, out_bytes = o_counts + (h_counts ? (size_t)m * 1024 : 0);
+    if ((rc = grow(&c->d_quart, &c->cap_quart, (size_t)m * 16)) != TQ_OK) return rc;
+    if ((rc = grow(&c->d_out, &c->cap_out, out_bytes)) != TQ_OK) return rc;
+    char *o = static_cast<char *>(c->d_out);
+    TQ_CUDA(cudaMemcpyAsync(c->d_quart, h_quartets, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
+    c->last_h2d += m * 16;
+    TQ_CUDA(cudaMemsetAsync(o + o_status, 0, 16, c->stream));
+    if ((rc = tq_resolve(c->plan, (const uint32_t *)c->d_planes, ntips, (const uint32_t *)c->d_quart, m, subsample,
+                         seed, (double *)(o + o_scor), (uint32_t *)(o + o_stat),
+                         h_counts ? (uint32_t *)(o + o_counts) : nullptr, (uint32_t *)(o + o_mr),
+                         (uint32_t *)(o + o_status), c->stream)) != TQ_OK)
+        return rc;
+    TQ_CUDA(cudaMemcpyAsync(h_rscor, o + o_scor, (size_t)m * 24, cudaMemcpyDeviceToHost, c->stream));
+    TQ_CUDA(cudaMemcpyAsync(h_rstat, o + o_stat, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    c->last_d2h += m * 32;
+    if (h_minrank) {
+        TQ_CUDA(cudaMemcpyAsync(h_minrank, o + o_mr, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+        c->last_d2h += m * 4;
+    }
+    if (h_counts) {
+        TQ_CUDA(cudaMemcpyAsync(h_counts, o + o_counts, (size_t)m * 1024, cudaMemcpyDeviceToHost, c->stream));
+        c->last_d2h += m * 1024;
+    }
+    TQ_CUDA(cudaStreamSynchronize(c->stream));
+    return TQ_OK;
+}
+
+int tq_microbench(int device, int kind, double *result)
+{
+    if (!result || kind < 0 || kind > 3) return fail(TQ_EINVAL, "tq_microbench: bad arguments");
+    DeviceGuard guard(device);
+    TQ_CUDA(tq::run_microbench(kind, result));
+    return TQ_OK;
+}
+
+}  // extern "C"

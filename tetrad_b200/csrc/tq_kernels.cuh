@@ -1,0 +1,34 @@
+// Internal declarations shared by tq_kernels.cu (device code + launchers) and tq_api.cu (C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tq {
+
+constexpr int kTileLoci  = 1024;  // loci per tile = 32 lanes x 32 bits
+constexpr int kTileWords = 32;    // uint4 {A,C,G,T} words per rank of a tile (one per lane)
+
+// Device-side view of a locus plan (see include/tetrad_b200.h, tq_plan_create).
+struct PlanDev {
+    const uint32_t *tile_off;   // [ntiles+1] offset of tile in a tip row, in uint4 units
+    const uint32_t *tile_k;     // [ntiles]   ranks (max locus length) of the tile
+    const uint32_t *loc_start;  // [ntiles*1024] first column of sorted locus l (pad: 0)
+    const uint32_t *loc_len;    // [ntiles*1024] columns of sorted locus l      (pad: 0)
+    int      ntiles;
+    uint32_t row_u4;            // uint4 per tip row
+};
+
+cudaError_t launch_pack(const PlanDev &plan, const uint8_t *d_tmparr, int64_t ntips,
+                        int64_t row_stride, uint32_t *d_planes, cudaStream_t stream);
+
+cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips,
+                           const uint32_t *d_quartets, int64_t m, bool subsample, uint64_t seed,
+                           double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
+                           uint32_t *d_minrank, uint32_t *d_status, int num_sms,
+                           cudaStream_t stream);
+
+cudaError_t run_microbench(int kind, double *result);
+
+extern int64_t g_launches;
+
+}  // namespace tq
