@@ -28,7 +28,6 @@ static constexpr int kWarps = 4;              // warps (= quartets in flight) pe
 static constexpr int kLdm = 18;               // padded column length of the smem matrices (doubles)
 static constexpr double kEps = 2.220446049250313e-16;
 static constexpr int kMaxSweeps = 30;
-static constexpr uint32_t kFlushEvery = 2047; // 2047 * 32 < 65536: 16-bit packed counters stay exact
 
 // ------------------------------------------------------------------------------------------
 // K1: pack
@@ -78,44 +77,100 @@ cudaError_t launch_pack(const PlanDev &plan, const uint8_t *d_tmparr, int64_t nt
 // ------------------------------------------------------------------------------------------
 // K3: counts
 // ------------------------------------------------------------------------------------------
-// acc[i] holds two 16-bit counters: pattern 2i (low half) and 2i+1 (high half), where
-// pattern p = 64a + 16b + 4c + d = 16*(4a+b) + (4c+d).
-__device__ __forceinline__ void accumulate256(const uint32_t (&A)[4], const uint32_t (&B)[4],
-                                              const uint32_t (&C)[4], const uint32_t (&D)[4],
-                                              uint32_t (&acc)[128])
+// One warp resolves one quartet.  Lane l owns locus word l of every tile (32 loci).
+//
+// stage 1 (subsample mode): the tip rows are streamed rank-chunk by rank-chunk (512 B per tip per
+//   chunk) through a per-warp cp.async ring in shared memory; for every chunk the lane forms
+//   sel = complete & segregating & ~taken and ORs the selected columns' one-hot bits into 16
+//   merged planes M (one SNP per locus, resolve_quartets.py:58-64).
+// stage 2: the 256 pattern counts of a tile are popc(A_a & B_b & C_c & D_d) on the merged planes.
+//   To halve the accumulator registers the two half-warps split the patterns: lanes 0-15 count
+//   a in {0,1}, lanes 16-31 count a in {2,3}, each for its own word and for the word of its
+//   partner lane (l ^ 16), whose planes arrive by 14 warp shuffles.
+//   acc[i] packs two 16-bit counters: patterns (a, b, cd=2h) and (a, b, cd=2h+1) with
+//   i = ((a & 1) * 4 + b) * 8 + h.  A lane adds at most 64 per call, the 16-lane butterfly of the
+//   flush multiplies by 16, so flushing every 63 calls keeps every field below 65536.
+static constexpr int kStages = 4;               // cp.async ring depth (rank-chunks in flight)
+static constexpr uint32_t kFlushEvery = 63;
+
+struct __align__(16) WarpScratch {
+    union {
+        uint4 ring[kStages][4][32];             // stage-1 staging: [stage][tip][lane]      8 KB
+        struct {
+            double M[3][16][kLdm];              // Jacobi columns M[m][col][row]
+            double nrm[3][16];                  // cached squared column norms (true scale)
+            double dsc[3][16];                  // column scale d   (true column = d * stored)
+            double esc[3][16];                  // 1 / d
+            double srt[3][16];
+        } svd;
+    };
+    uint32_t T[256];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
-    uint32_t CD[16];
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void accumulate128(uint32_t A0, uint32_t A1, const uint32_t (&B)[4],
+                                              const uint32_t (&C)[4], const uint32_t (&D)[4],
+                                              uint32_t (&acc)[64])
+{
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int d = 0; d < 4; ++d) CD[4 * c + d] = C[c] & D[d];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int ai = 0; ai < 2; ++ai)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const uint32_t ab = A[a] & B[b];
+            const uint32_t ab = (ai ? A1 : A0) & B[b];
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
-                const uint32_t p0 = __popc(ab & CD[2 * h]);
-                const uint32_t p1 = __popc(ab & CD[2 * h + 1]);
-                acc[(4 * a + b) * 8 + h] += p0 + (p1 << 16);
+                const uint32_t p0 = __popc(ab & C[h >> 1] & D[2 * (h & 1)]);
+                const uint32_t p1 = __popc(ab & C[h >> 1] & D[2 * (h & 1) + 1]);
+                acc[(ai * 4 + b) * 8 + h] += p0 + (p1 << 16);
             }
         }
 }
 
-// Warp-reduce the packed per-lane counters into the warp's T[256] (shared memory), then clear.
-__device__ __forceinline__ void flush_acc(uint32_t (&acc)[128], uint32_t *T, int lane)
+// 256 pattern counts of one tile word pair (own word + partner lane's word), split by half-warp.
+__device__ __forceinline__ void count_tile(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                           const uint32_t (&MC)[4], const uint32_t (&MD)[4],
+                                           bool upper, uint32_t (&acc)[64])
 {
+    // planes the partner needs from me: the a-planes of ITS half, and all of B, C, D
+    const uint32_t sendA0 = upper ? MA[0] : MA[2], sendA1 = upper ? MA[1] : MA[3];
+    const uint32_t pA0 = __shfl_xor_sync(kFull, sendA0, 16), pA1 = __shfl_xor_sync(kFull, sendA1, 16);
+    uint32_t pB[4], pC[4], pD[4];
 #pragma unroll
-    for (int i = 0; i < 128; ++i) {
-        const uint32_t lo = __reduce_add_sync(kFull, acc[i] & 0xFFFFu);
-        const uint32_t hi = __reduce_add_sync(kFull, acc[i] >> 16);
-        if (lane == 0) {
-            uint2 *t = reinterpret_cast<uint2 *>(T + 2 * i);
-            uint2 v = *t;
-            v.x += lo;
-            v.y += hi;
-            *t = v;
+    for (int i = 0; i < 4; ++i) {
+        pB[i] = __shfl_xor_sync(kFull, MB[i], 16);
+        pC[i] = __shfl_xor_sync(kFull, MC[i], 16);
+        pD[i] = __shfl_xor_sync(kFull, MD[i], 16);
+    }
+    accumulate128(upper ? MA[2] : MA[0], upper ? MA[3] : MA[1], MB, MC, MD, acc);
+    accumulate128(pA0, pA1, pB, pC, pD, acc);
+}
+
+// Butterfly-add the packed counters over the 16 lanes of each half-warp, add into T, clear.
+__device__ __forceinline__ void flush_acc(uint32_t (&acc)[64], uint32_t *T, int lane)
+{
+    const int abase = (lane >> 4) * 2;           // first a-value of this half-warp
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        uint32_t v = acc[i];
+        v += __shfl_xor_sync(kFull, v, 8);
+        v += __shfl_xor_sync(kFull, v, 4);
+        v += __shfl_xor_sync(kFull, v, 2);
+        v += __shfl_xor_sync(kFull, v, 1);
+        if ((lane & 15) == (i & 15)) {
+            const int ai = i >> 5, b = (i >> 3) & 3, h = i & 7;
+            uint2 *t = reinterpret_cast<uint2 *>(T + ((abase + ai) * 4 + b) * 16 + 2 * h);
+            uint2 cur = *t;
+            cur.x += v & 0xFFFFu;
+            cur.y += v >> 16;
+            *t = cur;
         }
         acc[i] = 0u;
     }
@@ -125,28 +180,48 @@ template <bool kSubsample>
 __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *__restrict__ r0,
                                               const uint4 *__restrict__ r1,
                                               const uint4 *__restrict__ r2,
-                                              const uint4 *__restrict__ r3, uint32_t *T, int lane)
+                                              const uint4 *__restrict__ r3, WarpScratch &ws, int lane)
 {
-    uint32_t acc[128];
+    uint32_t acc[64];
 #pragma unroll
-    for (int i = 0; i < 128; ++i) acc[i] = 0u;
-    uint32_t pending = 0;   // accumulate256 calls since the last flush (each adds <= 32 per counter)
+    for (int i = 0; i < 64; ++i) acc[i] = 0u;
+    const bool upper = lane >= 16;
+    uint32_t pending = 0;
+    const uint32_t nchunks = plan.row_u4 / kTileWords;
 
+    // prologue: chunks 0 .. kStages-2 in flight
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if ((uint32_t)s < nchunks) {
+            const uint32_t o = s * kTileWords + lane;
+            cp_async16(&ws.ring[s][0][lane], r0 + o); cp_async16(&ws.ring[s][1][lane], r1 + o);
+            cp_async16(&ws.ring[s][2][lane], r2 + o); cp_async16(&ws.ring[s][3][lane], r3 + o);
+        }
+        cp_async_commit();
+    }
+
+    uint32_t u = 0;                                   // rank-chunk index along the rows
     for (int tile = 0; tile < plan.ntiles; ++tile) {
-        const uint32_t off = __ldg(plan.tile_off + tile) + lane;
         const uint32_t K = __ldg(plan.tile_k + tile);
-        if (kSubsample) {
-            // stage 1: lowest rank whose column is complete and segregating for this quartet
-            uint32_t taken = 0u;
-            uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
-            uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
-            uint4 a = __ldg(r0 + off), b = __ldg(r1 + off), c = __ldg(r2 + off), d = __ldg(r3 + off);
-            for (uint32_t k = 0; k < K; ++k) {
-                uint4 na = a, nb = b, nc = c, nd = d;
-                if (k + 1 < K) {
-                    const uint32_t o2 = off + (k + 1) * kTileWords;
-                    na = __ldg(r0 + o2); nb = __ldg(r1 + o2); nc = __ldg(r2 + o2); nd = __ldg(r3 + o2);
+        uint32_t taken = 0u;
+        uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
+        uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
+        for (uint32_t k = 0; k < K; ++k, ++u) {
+            {   // keep kStages-1 chunks in flight
+                const uint32_t nu = u + kStages - 1;
+                if (nu < nchunks) {
+                    const uint32_t o = nu * kTileWords + lane;
+                    const int s = nu % kStages;
+                    cp_async16(&ws.ring[s][0][lane], r0 + o); cp_async16(&ws.ring[s][1][lane], r1 + o);
+                    cp_async16(&ws.ring[s][2][lane], r2 + o); cp_async16(&ws.ring[s][3][lane], r3 + o);
                 }
+                cp_async_commit();
+            }
+            cp_async_wait<kStages - 1>();
+            const int s = u % kStages;
+            const uint4 a = ws.ring[s][0][lane], b = ws.ring[s][1][lane];
+            const uint4 c = ws.ring[s][2][lane], d = ws.ring[s][3][lane];
+            if (kSubsample) {
                 const uint32_t valid = (a.x | a.y | a.z | a.w) & (b.x | b.y | b.z | b.w) &
                                        (c.x | c.y | c.z | c.w) & (d.x | d.y | d.z | d.w);
                 const uint32_t same = (a.x & b.x & c.x & d.x) | (a.y & b.y & c.y & d.y) |
@@ -157,37 +232,32 @@ __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *
                 MB[0] |= b.x & sel; MB[1] |= b.y & sel; MB[2] |= b.z & sel; MB[3] |= b.w & sel;
                 MC[0] |= c.x & sel; MC[1] |= c.y & sel; MC[2] |= c.z & sel; MC[3] |= c.w & sel;
                 MD[0] |= d.x & sel; MD[1] |= d.y & sel; MD[2] |= d.z & sel; MD[3] |= d.w & sel;
-                a = na; b = nb; c = nc; d = nd;
-            }
-            // stage 2: 256 pattern counts over the tile's 1024 loci
-            accumulate256(MA, MB, MC, MD, acc);
-            if (++pending == kFlushEvery) { flush_acc(acc, T, lane); pending = 0; }
-        } else {
-            for (uint32_t k = 0; k < K; ++k) {
-                const uint32_t o = off + k * kTileWords;
-                const uint4 a = __ldg(r0 + o), b = __ldg(r1 + o), c = __ldg(r2 + o), d = __ldg(r3 + o);
+            } else {
+                // full mode (resolve_quartets.py:92-95): every complete column counts; the four
+                // invariant patterns aaaa are zeroed by the caller
                 const uint32_t A[4] = {a.x, a.y, a.z, a.w}, B[4] = {b.x, b.y, b.z, b.w};
                 const uint32_t C[4] = {c.x, c.y, c.z, c.w}, D[4] = {d.x, d.y, d.z, d.w};
-                accumulate256(A, B, C, D, acc);
-                if (++pending == kFlushEvery) { flush_acc(acc, T, lane); pending = 0; }
+                count_tile(A, B, C, D, upper, acc);
+                if (++pending == kFlushEvery) { flush_acc(acc, ws.T, lane); pending = 0; }
             }
         }
+        if (kSubsample) {
+            count_tile(MA, MB, MC, MD, upper, acc);
+            if (++pending == kFlushEvery) { flush_acc(acc, ws.T, lane); pending = 0; }
+        }
     }
-    flush_acc(acc, T, lane);
+    cp_async_wait<0>();
+    flush_acc(acc, ws.T, lane);
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: scores.  One-sided (Hestenes) Jacobi on the three 16x16 flattenings, columns in shared
-// memory, lane (m, s) = (lane / 8, lane % 8) rotates pair s of matrix m in each of the 15
-// rounds of a round-robin sweep.
+// K4: scores.  One-sided (Hestenes) Jacobi on the three 16x16 flattenings with fast scaled
+// rotations: the true column i is dsc[i] * M[.][i][.]; a rotation by tangent t of the true pair
+// (X, Y) -> (c (X - t Y), c (Y + t X)) only touches the stored columns with two FMAs per row
+// and multiplies both scales by c.  Lane (m, s) = (lane / 8, lane % 8) handles pair s of
+// matrix m in each of the 15 rounds of a round-robin sweep.  The tangent is computed in FP32
+// (a slightly-off angle only slows convergence); c = rsqrt(1 + t^2) and its inverse in FP64.
 // ------------------------------------------------------------------------------------------
-struct __align__(16) WarpScratch {
-    uint32_t T[256];
-    double M[3][16][kLdm];   // M[m][col][row]
-    double sv[3][16];
-    double srt[3][16];
-};
-
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 {
     x += 0x9E3779B97F4A7C15ull;
@@ -196,119 +266,155 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
     return x ^ (x >> 31);
 }
 
-__device__ __forceinline__ void svd_scores(WarpScratch &ws, int lane, double (&score)[3],
-                                           uint32_t &best, uint32_t &minrank)
+static constexpr double kTau2 = 1e-18;    // rotate when gamma^2 > tau^2 * |x|^2 |y|^2  (tau = 1e-9)
+static constexpr double kStop2 = 1e-8;    // a sweep whose largest relative gamma was < 1e-4 is the last
+
+__device__ __noinline__ void svd_scores(WarpScratch &ws, int lane, double *score_out, uint32_t *best_out,
+                                        uint32_t *minrank_out)
 {
-    // the three flattenings (resolve_quartets.py:63,67-72), stored column-major
+    auto &sv = ws.svd;
+    // T -> registers first: the SVD scratch overlays the cp.async ring, not T, but M is filled
+    // from every lane's 8 entries, so read them all before anyone writes
+    double v[8];
     double fro2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[i] = (double)ws.T[lane + 32 * i];
+        fro2 = fma(v[i], v[i], fro2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fro2 += __shfl_xor_sync(kFull, fro2, o);
+    const double tiny = (kEps * kEps) * fro2;       // columns this small are null directions
+    __syncwarp();
+    // the three flattenings (resolve_quartets.py:63,67-72), stored column-major
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int p = lane + 32 * i;
         const int a = p >> 6, b = (p >> 4) & 3, c = (p >> 2) & 3, d = p & 3;
-        const double v = (double)ws.T[p];
-        fro2 += v * v;
-        ws.M[0][4 * c + d][4 * a + b] = v;   // rows (a,b), cols (c,d)
-        ws.M[1][4 * b + d][4 * a + c] = v;   // rows (a,c), cols (b,d)
-        ws.M[2][4 * b + c][4 * a + d] = v;   // rows (a,d), cols (b,c)
+        sv.M[0][4 * c + d][4 * a + b] = v[i];       // rows (a,b), cols (c,d)
+        sv.M[1][4 * b + d][4 * a + c] = v[i];       // rows (a,c), cols (b,d)
+        sv.M[2][4 * b + c][4 * a + d] = v[i];       // rows (a,d), cols (b,c)
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) fro2 += __shfl_xor_sync(kFull, fro2, o);
-    const double tiny = (kEps * kEps) * fro2;   // columns this small are null directions
+    for (int c = lane; c < 48; c += 32) { (&sv.dsc[0][0])[c] = 1.0; (&sv.esc[0][0])[c] = 1.0; }
     __syncwarp();
 
     const int m = lane >> 3, s = lane & 7;
     const bool active = lane < 24;
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
-        bool rotated = false;
+        // refresh the cached norms from the columns
+        for (int c = lane; c < 48; c += 32) {
+            const double2 *col = reinterpret_cast<const double2 *>(&sv.M[c >> 4][c & 15][0]);
+            double n2 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { const double2 x = col[r]; n2 = fma(x.x, x.x, n2); n2 = fma(x.y, x.y, n2); }
+            const double dd = (&sv.dsc[0][0])[c];
+            (&sv.nrm[0][0])[c] = n2 * dd * dd;
+        }
+        __syncwarp();
+        bool big = false;
         for (int rnd = 0; rnd < 15; ++rnd) {
             if (active) {
                 int i, j;
                 if (s == 0) { i = 15; j = rnd; }
-                else { i = (rnd + s) % 15; j = (rnd + 15 - s) % 15; }
-                double2 *ci = reinterpret_cast<double2 *>(&ws.M[m][i][0]);
-                double2 *cj = reinterpret_cast<double2 *>(&ws.M[m][j][0]);
-                double2 x[8], y[8];
+                else { i = rnd + s; i -= (i >= 15) ? 15 : 0; j = rnd + 15 - s; j -= (j >= 15) ? 15 : 0; }
+                const double al = sv.nrm[m][i], be = sv.nrm[m][j];
+                if (al > tiny && be > tiny) {
+                    double2 *ci = reinterpret_cast<double2 *>(&sv.M[m][i][0]);
+                    double2 *cj = reinterpret_cast<double2 *>(&sv.M[m][j][0]);
+                    double2 x[8], y[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) { x[r] = ci[r]; y[r] = cj[r]; }
-                double al = 0.0, be = 0.0, ga = 0.0;
+                    for (int r = 0; r < 8; ++r) { x[r] = ci[r]; y[r] = cj[r]; }
+                    double g0 = 0.0, g1 = 0.0;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    al = fma(x[r].x, x[r].x, al); al = fma(x[r].y, x[r].y, al);
-                    be = fma(y[r].x, y[r].x, be); be = fma(y[r].y, y[r].y, be);
-                    ga = fma(x[r].x, y[r].x, ga); ga = fma(x[r].y, y[r].y, ga);
-                }
-                if (al > tiny && be > tiny && fabs(ga) > (2.0 * kEps) * sqrt(al * be)) {
-                    const double zeta = (be - al) / (2.0 * ga);
-                    const double az = fabs(zeta);
-                    double t = (az < 1e100) ? 1.0 / (az + sqrt(1.0 + zeta * zeta)) : 0.5 / az;
-                    t = (zeta < 0.0) ? -t : t;
-                    const double cs = 1.0 / sqrt(1.0 + t * t);
-                    const double sn = cs * t;
+                    for (int r = 0; r < 8; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
+                    const double di = sv.dsc[m][i], dj = sv.dsc[m][j];
+                    const double ga = (g0 + g1) * di * dj;
+                    const double ab = al * be, g2 = ga * ga;
+                    if (g2 > kTau2 * ab) {
+                        big |= g2 > kStop2 * ab;
+                        // tangent of the rotation angle, FP32 is enough
+                        const float zf = (float)(be - al) / (2.0f * (float)ga);
+                        const float az = fabsf(zf);
+                        float tf = (az < 1e9f) ? __frcp_rn(az + sqrtf(fmaf(zf, zf, 1.0f))) : 0.5f / az;
+                        if (!(az == az)) tf = 1.0f;                    // be == al and ga tiny: 45 degrees
+                        const double t = (zf < 0.0f) ? -(double)tf : (double)tf;
+                        const double w = fma(t, t, 1.0);
+                        const double cs = rsqrt(w);                    // cos
+                        const double ei = sv.esc[m][i], ej = sv.esc[m][j];
+                        const double rx = t * dj * ei, ry = t * di * ej;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        double2 nx, ny;
-                        nx.x = cs * x[r].x - sn * y[r].x; nx.y = cs * x[r].y - sn * y[r].y;
-                        ny.x = sn * x[r].x + cs * y[r].x; ny.y = sn * x[r].y + cs * y[r].y;
-                        ci[r] = nx; cj[r] = ny;
+                        for (int r = 0; r < 8; ++r) {
+                            double2 nx, ny;
+                            nx.x = fma(-rx, y[r].x, x[r].x); nx.y = fma(-rx, y[r].y, x[r].y);
+                            ny.x = fma(ry, x[r].x, y[r].x);  ny.y = fma(ry, x[r].y, y[r].y);
+                            ci[r] = nx; cj[r] = ny;
+                        }
+                        const double sec = w * cs;                     // 1 / cos
+                        sv.dsc[m][i] = di * cs; sv.dsc[m][j] = dj * cs;
+                        sv.esc[m][i] = ei * sec; sv.esc[m][j] = ej * sec;
+                        sv.nrm[m][i] = fmax(al - t * ga, 0.0);
+                        sv.nrm[m][j] = be + t * ga;
                     }
-                    rotated = true;
                 }
             }
             __syncwarp();
         }
-        if (!__any_sync(kFull, rotated)) break;
+        if (!__any_sync(kFull, big)) break;
     }
 
-    // singular values = column norms; sort descending per matrix by rank counting
+    // singular values = true column norms; sort descending per matrix by rank counting
     for (int c = lane; c < 48; c += 32) {
-        const double *col = &ws.M[c >> 4][c & 15][0];
+        const double *col = &sv.M[c >> 4][c & 15][0];
         double n2 = 0.0;
 #pragma unroll
         for (int r = 0; r < 16; ++r) n2 = fma(col[r], col[r], n2);
-        ws.sv[c >> 4][c & 15] = sqrt(n2);
+        (&sv.nrm[0][0])[c] = sqrt(n2) * (&sv.dsc[0][0])[c];
     }
     __syncwarp();
     for (int c = lane; c < 48; c += 32) {
         const int mm = c >> 4, col = c & 15;
-        const double v = ws.sv[mm][col];
+        const double val = sv.nrm[mm][col];
         int pos = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const double u = ws.sv[mm][j];
-            pos += (u > v || (u == v && j < col)) ? 1 : 0;
+            const double u = sv.nrm[mm][j];
+            pos += (u > val || (u == val && j < col)) ? 1 : 0;
         }
-        ws.srt[mm][pos] = v;
+        sv.srt[mm][pos] = val;
     }
     __syncwarp();
     // rank = #{sigma > sigma_max * 16 * eps} (numpy.linalg.matrix_rank), :243
     int rank = 16;
     if (lane < 3) {
-        const double tol = ws.srt[lane][0] * (16.0 * kEps);
+        const double tol = sv.srt[lane][0] * (16.0 * kEps);
         rank = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rank += (ws.srt[lane][j] > tol) ? 1 : 0;
+        for (int j = 0; j < 16; ++j) rank += (sv.srt[lane][j] > tol) ? 1 : 0;
     }
     int mr = min(__shfl_sync(kFull, rank, 0), min(__shfl_sync(kFull, rank, 1), __shfl_sync(kFull, rank, 2)));
     mr = min(mr, 10);                                                  // :246
     double sc = 0.0;
     if (lane < 3) {
-        for (int j = mr; j < 16; ++j) sc = fma(ws.srt[lane][j], ws.srt[lane][j], sc);
+        for (int j = mr; j < 16; ++j) sc = fma(sv.srt[lane][j], sv.srt[lane][j], sc);
         sc = sqrt(sc);                                                 // :248
     }
-    score[0] = __shfl_sync(kFull, sc, 0);
-    score[1] = __shfl_sync(kFull, sc, 1);
-    score[2] = __shfl_sync(kFull, sc, 2);
-    best = 0;                                                          // first argmin, :251
-    if (score[1] < score[best]) best = 1;
-    if (score[2] < score[best]) best = 2;
-    minrank = (uint32_t)mr;
+    const double s0 = __shfl_sync(kFull, sc, 0), s1 = __shfl_sync(kFull, sc, 1), s2 = __shfl_sync(kFull, sc, 2);
+    uint32_t best = 0;                                                 // first argmin, :251
+    double lo = s0;
+    if (s1 < lo) { best = 1; lo = s1; }
+    if (s2 < lo) { best = 2; }
+    score_out[0] = s0; score_out[1] = s1; score_out[2] = s2;
+    *best_out = best;
+    *minrank_out = (uint32_t)mr;
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
-// fused resolve kernel: one warp per quartet, persistent grid-stride over quartets
+// fused resolve kernel: one warp per quartet, persistent grid-stride over groups of kWarps
+// consecutive quartets (neighbours in lexicographic order share tips -> L1 hits)
 // ------------------------------------------------------------------------------------------
 template <bool kSubsample>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32, 4)
 resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
                const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
                double *__restrict__ rscor, uint2 *__restrict__ rstat,
@@ -337,7 +443,7 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
         count_quartet<kSubsample>(plan, planes + (size_t)t.x * plan.row_u4,
                                   planes + (size_t)t.y * plan.row_u4,
                                   planes + (size_t)t.z * plan.row_u4,
-                                  planes + (size_t)t.w * plan.row_u4, ws.T, lane);
+                                  planes + (size_t)t.w * plan.row_u4, ws, lane);
         __syncwarp();
         if (!kSubsample && lane < 4) ws.T[85u * lane] = 0u;   // invariant patterns aaaa, :218
         __syncwarp();
@@ -358,7 +464,7 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
             h = splitmix64(h ^ t.z); h = splitmix64(h ^ t.w);
             best = (uint32_t)(h % 3ull);                                // stands in for :231
         } else {
-            svd_scores(ws, lane, score, best, minrank);
+            svd_scores(ws, lane, score, &best, &minrank);
         }
         if (lane == 0) {
             rscor[3 * q] = score[0]; rscor[3 * q + 1] = score[1]; rscor[3 * q + 2] = score[2];
@@ -377,7 +483,7 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
 {
     if (m == 0) return cudaSuccess;
     const int64_t want = (m + kWarps - 1) / kWarps;
-    const int64_t cap = (int64_t)num_sms * 2;          // 2 resident CTAs per SM (launch bounds)
+    const int64_t cap = (int64_t)num_sms * 4;          // 4 resident CTAs per SM (launch bounds)
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     const uint4 *planes = reinterpret_cast<const uint4 *>(d_planes);
     const uint4 *quartets = reinterpret_cast<const uint4 *>(d_quartets);
