@@ -242,6 +242,8 @@ int tq_resolve(const tq_plan *plan, const uint32_t *d_planes, int64_t ntips,
     if (m == 0) return TQ_OK;
     if (!d_quartets || !d_rscor || !d_rstat) return fail(TQ_EINVAL, "tq_resolve: NULL device pointer");
     if (plan->row_u4 > 0 && !d_planes) return fail(TQ_EINVAL, "tq_resolve: d_planes is NULL");
+    if ((uint64_t)ntips * (uint64_t)plan->row_u4 >= ((uint64_t)1 << 32))
+        return fail(TQ_EINVAL, "tq_resolve: packed matrix exceeds 2^32 x 16 bytes (ntips * row_words too large)");
     if (((uintptr_t)d_planes & 15u) || ((uintptr_t)d_quartets & 15u) || ((uintptr_t)d_rstat & 7u))
         return fail(TQ_EINVAL, "tq_resolve: planes/quartets must be 16-byte and rstat 8-byte aligned");
     DeviceGuard guard(plan->device);

@@ -176,11 +176,21 @@ __device__ __forceinline__ void flush_acc(uint32_t (&acc)[64], uint32_t *T, int 
     }
 }
 
+// Issue the four 16-byte cp.async of rank-chunk `nu` (one per tip) into ring stage nu % kStages.
+// All global addressing is a 32-bit uint4 index off `planes` (the host checks ntips*row_u4 < 2^32).
+__device__ __forceinline__ void issue_chunk(uint32_t ring_s, const uint4 *__restrict__ planes, uint32_t lane_nu,
+                                            uint32_t stage, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3)
+{
+    const uint32_t s = ring_s + stage * (4 * 32 * 16);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(planes + (t0 + lane_nu)) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 512), "l"(planes + (t1 + lane_nu)) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1024), "l"(planes + (t2 + lane_nu)) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1536), "l"(planes + (t3 + lane_nu)) : "memory");
+}
+
 template <bool kSubsample>
-__device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *__restrict__ r0,
-                                              const uint4 *__restrict__ r1,
-                                              const uint4 *__restrict__ r2,
-                                              const uint4 *__restrict__ r3, WarpScratch &ws, int lane)
+__device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *__restrict__ planes,
+                                              uint4 tips, WarpScratch &ws, int lane)
 {
     uint32_t acc[64];
 #pragma unroll
@@ -188,15 +198,14 @@ __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *
     const bool upper = lane >= 16;
     uint32_t pending = 0;
     const uint32_t nchunks = plan.row_u4 / kTileWords;
+    const uint32_t t0 = tips.x * plan.row_u4, t1 = tips.y * plan.row_u4;    // row starts, uint4 units
+    const uint32_t t2 = tips.z * plan.row_u4, t3 = tips.w * plan.row_u4;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&ws.ring[0][0][lane]);
 
     // prologue: chunks 0 .. kStages-2 in flight
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
-        if ((uint32_t)s < nchunks) {
-            const uint32_t o = s * kTileWords + lane;
-            cp_async16(&ws.ring[s][0][lane], r0 + o); cp_async16(&ws.ring[s][1][lane], r1 + o);
-            cp_async16(&ws.ring[s][2][lane], r2 + o); cp_async16(&ws.ring[s][3][lane], r3 + o);
-        }
+        if ((uint32_t)s < nchunks) issue_chunk(ring_s, planes, s * kTileWords + lane, s, t0, t1, t2, t3);
         cp_async_commit();
     }
 
@@ -209,12 +218,7 @@ __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *
         for (uint32_t k = 0; k < K; ++k, ++u) {
             {   // keep kStages-1 chunks in flight
                 const uint32_t nu = u + kStages - 1;
-                if (nu < nchunks) {
-                    const uint32_t o = nu * kTileWords + lane;
-                    const int s = nu % kStages;
-                    cp_async16(&ws.ring[s][0][lane], r0 + o); cp_async16(&ws.ring[s][1][lane], r1 + o);
-                    cp_async16(&ws.ring[s][2][lane], r2 + o); cp_async16(&ws.ring[s][3][lane], r3 + o);
-                }
+                if (nu < nchunks) issue_chunk(ring_s, planes, nu * kTileWords + lane, nu % kStages, t0, t1, t2, t3);
                 cp_async_commit();
             }
             cp_async_wait<kStages - 1>();
@@ -300,62 +304,77 @@ __device__ __noinline__ void svd_scores(WarpScratch &ws, int lane, double *score
 
     const int m = lane >> 3, s = lane & 7;
     const bool active = lane < 24;
+    double *const Mm = &sv.M[active ? m : 0][0][0];          // columns of this lane's matrix
+    double *const nrm = &sv.nrm[active ? m : 0][0];
+    double *const dsc = &sv.dsc[active ? m : 0][0];
+    double *const esc = &sv.esc[active ? m : 0][0];
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         // refresh the cached norms from the columns
         for (int c = lane; c < 48; c += 32) {
             const double2 *col = reinterpret_cast<const double2 *>(&sv.M[c >> 4][c & 15][0]);
-            double n2 = 0.0;
+            double n0 = 0.0, n1 = 0.0;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) { const double2 x = col[r]; n2 = fma(x.x, x.x, n2); n2 = fma(x.y, x.y, n2); }
+            for (int r = 0; r < 8; ++r) { const double2 x = col[r]; n0 = fma(x.x, x.x, n0); n1 = fma(x.y, x.y, n1); }
             const double dd = (&sv.dsc[0][0])[c];
-            (&sv.nrm[0][0])[c] = n2 * dd * dd;
+            (&sv.nrm[0][0])[c] = (n0 + n1) * dd * dd;
         }
         __syncwarp();
         bool big = false;
+        // round-robin pairing of 16 columns: slot 0 holds (15, rnd); slot s holds
+        // ((rnd + s) mod 15, (rnd - s) mod 15); i and j advance by one (mod 15) per round
+        int i = (s == 0) ? 15 : s, j = (s == 0) ? 0 : 15 - s;
         for (int rnd = 0; rnd < 15; ++rnd) {
             if (active) {
-                int i, j;
-                if (s == 0) { i = 15; j = rnd; }
-                else { i = rnd + s; i -= (i >= 15) ? 15 : 0; j = rnd + 15 - s; j -= (j >= 15) ? 15 : 0; }
-                const double al = sv.nrm[m][i], be = sv.nrm[m][j];
-                if (al > tiny && be > tiny) {
-                    double2 *ci = reinterpret_cast<double2 *>(&sv.M[m][i][0]);
-                    double2 *cj = reinterpret_cast<double2 *>(&sv.M[m][j][0]);
-                    double2 x[8], y[8];
+                const double al = nrm[i], be = nrm[j];
+                double2 *ci = reinterpret_cast<double2 *>(Mm + i * kLdm);
+                double2 *cj = reinterpret_cast<double2 *>(Mm + j * kLdm);
+                double2 x[8], y[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) { x[r] = ci[r]; y[r] = cj[r]; }
-                    double g0 = 0.0, g1 = 0.0;
+                for (int r = 0; r < 8; ++r) { x[r] = ci[r]; y[r] = cj[r]; }
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) { g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1); }
-                    const double di = sv.dsc[m][i], dj = sv.dsc[m][j];
-                    const double ga = (g0 + g1) * di * dj;
-                    const double ab = al * be, g2 = ga * ga;
-                    if (g2 > kTau2 * ab) {
-                        big |= g2 > kStop2 * ab;
-                        // tangent of the rotation angle, FP32 is enough
-                        const float zf = (float)(be - al) / (2.0f * (float)ga);
-                        const float az = fabsf(zf);
-                        float tf = (az < 1e9f) ? __frcp_rn(az + sqrtf(fmaf(zf, zf, 1.0f))) : 0.5f / az;
-                        if (!(az == az)) tf = 1.0f;                    // be == al and ga tiny: 45 degrees
-                        const double t = (zf < 0.0f) ? -(double)tf : (double)tf;
-                        const double w = fma(t, t, 1.0);
-                        const double cs = rsqrt(w);                    // cos
-                        const double ei = sv.esc[m][i], ej = sv.esc[m][j];
-                        const double rx = t * dj * ei, ry = t * di * ej;
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) {
-                            double2 nx, ny;
-                            nx.x = fma(-rx, y[r].x, x[r].x); nx.y = fma(-rx, y[r].y, x[r].y);
-                            ny.x = fma(ry, x[r].x, y[r].x);  ny.y = fma(ry, x[r].y, y[r].y);
-                            ci[r] = nx; cj[r] = ny;
-                        }
-                        const double sec = w * cs;                     // 1 / cos
-                        sv.dsc[m][i] = di * cs; sv.dsc[m][j] = dj * cs;
-                        sv.esc[m][i] = ei * sec; sv.esc[m][j] = ej * sec;
-                        sv.nrm[m][i] = fmax(al - t * ga, 0.0);
-                        sv.nrm[m][j] = be + t * ga;
-                    }
+                for (int r = 0; r < 8; r += 2) {
+                    g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1);
+                    g2 = fma(x[r + 1].x, y[r + 1].x, g2); g3 = fma(x[r + 1].y, y[r + 1].y, g3);
                 }
+                const double di = dsc[i], dj = dsc[j];
+                const double ga = ((g0 + g1) + (g2 + g3)) * (di * dj);
+                const double ab = al * be, gg = ga * ga;
+                const bool rot = al > tiny && be > tiny && gg > kTau2 * ab;
+                if (rot) {
+                    big |= gg > kStop2 * ab;
+                    // tangent t = sign(z) / (|z| + sqrt(1 + z^2)), z = (be - al) / (2 ga): approximate
+                    // arithmetic is enough (a slightly-off angle only slows convergence)
+                    double inv2g;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv2g) : "d"(ga + ga));
+                    const double z = (be - al) * inv2g;
+                    const float az = fminf(fabsf((float)z), 1e18f);
+                    const float w1 = fmaf(az, az, 1.0f);
+                    const float tf = __fdividef(1.0f, az + w1 * rsqrtf(w1));
+                    const double t = (z < 0.0) ? -(double)tf : (double)tf;
+                    // c = 1 / sqrt(1 + t^2) to full precision: approximate rsqrt + 2 Newton steps
+                    const double w = fma(t, t, 1.0);
+                    double cs;
+                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(cs) : "d"(w));
+                    cs = cs * fma(-0.5 * w, cs * cs, 1.5);
+                    cs = cs * fma(-0.5 * w, cs * cs, 1.5);
+                    const double ei = esc[i], ej = esc[j];
+                    const double rx = -(t * dj) * ei, ry = (t * di) * ej;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        double2 nx, ny;
+                        nx.x = fma(rx, y[r].x, x[r].x); nx.y = fma(rx, y[r].y, x[r].y);
+                        ny.x = fma(ry, x[r].x, y[r].x); ny.y = fma(ry, x[r].y, y[r].y);
+                        ci[r] = nx; cj[r] = ny;
+                    }
+                    const double sec = w * cs;                         // 1 / cos
+                    const double tg = t * ga;
+                    dsc[i] = di * cs; dsc[j] = dj * cs;
+                    esc[i] = ei * sec; esc[j] = ej * sec;
+                    nrm[i] = al - tg; nrm[j] = be + tg;
+                }
+                if (s != 0) i = (i == 14) ? 0 : i + 1;
+                j = (j == 14) ? 0 : j + 1;
             }
             __syncwarp();
         }
@@ -440,10 +459,7 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
 #pragma unroll
         for (int i = 0; i < 8; ++i) ws.T[lane + 32 * i] = 0u;
         __syncwarp();
-        count_quartet<kSubsample>(plan, planes + (size_t)t.x * plan.row_u4,
-                                  planes + (size_t)t.y * plan.row_u4,
-                                  planes + (size_t)t.z * plan.row_u4,
-                                  planes + (size_t)t.w * plan.row_u4, ws, lane);
+        count_quartet<kSubsample>(plan, planes, t, ws, lane);
         __syncwarp();
         if (!kSubsample && lane < 4) ws.T[85u * lane] = 0u;   // invariant patterns aaaa, :218
         __syncwarp();
