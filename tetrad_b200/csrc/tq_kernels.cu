@@ -19,11 +19,17 @@
 // "lowest rank k whose bit survives the quartet's mask" -- a running OR per lane.
 #include "tq_kernels.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace tq {
 
 int64_t g_launches = 0;
 
 static constexpr unsigned kFull = 0xFFFFFFFFu;
+#ifndef TQ_MIN_CTAS
+#define TQ_MIN_CTAS 4                         // resident CTAs per SM the register budget is sized for
+#endif
 static constexpr int kWarps = 4;              // warps (= quartets in flight) per CTA
 static constexpr int kLdm = 18;               // padded column length of the smem matrices (doubles)
 static constexpr double kEps = 2.220446049250313e-16;
@@ -90,17 +96,23 @@ cudaError_t launch_pack(const PlanDev &plan, const uint8_t *d_tmparr, int64_t nt
 //   acc[i] packs two 16-bit counters: patterns (a, b, cd=2h) and (a, b, cd=2h+1) with
 //   i = ((a & 1) * 4 + b) * 8 + h.  A lane adds at most 64 per call, the 16-lane butterfly of the
 //   flush multiplies by 16, so flushing every 63 calls keeps every field below 65536.
-static constexpr int kStages = 4;               // cp.async ring depth (rank-chunks in flight)
+#ifdef TQ_PHASE_TIMERS
+__device__ unsigned long long g_phase_clk[8];
+#define TQ_T0() long long tq_t0 = clock64()
+#define TQ_ACC(i) do { long long tq_t1 = clock64(); ph[i] += tq_t1 - tq_t0; tq_t0 = tq_t1; } while (0)
+#else
+#define TQ_T0()
+#define TQ_ACC(i)
+#endif
+static constexpr int kStages = 4;               // cp.async ring depth (rank-chunks in flight); 6 was slower (L1 shrinks)
 static constexpr uint32_t kFlushEvery = 63;
 
 struct __align__(16) WarpScratch {
     union {
         uint4 ring[kStages][4][32];             // stage-1 staging: [stage][tip][lane]      8 KB
         struct {
-            double M[3][16][kLdm];              // Jacobi columns M[m][col][row]
-            double nrm[3][16];                  // cached squared column norms (true scale)
-            double dsc[3][16];                  // column scale d   (true column = d * stored)
-            double esc[3][16];                  // 1 / d
+            double M[3][16][kLdm];              // flattenings M[m][col][row]; later the exchange buffer
+            double nrm[3][16];                  // singular values
             double srt[3][16];
         } svd;
     };
@@ -190,8 +202,13 @@ __device__ __forceinline__ void issue_chunk(uint32_t ring_s, const uint4 *__rest
 
 template <bool kSubsample>
 __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *__restrict__ planes,
-                                              uint4 tips, WarpScratch &ws, int lane)
+                                              uint4 tips, WarpScratch &ws, int lane, uint32_t debug
+#ifdef TQ_PHASE_TIMERS
+                                              , long long (&ph)[8]
+#endif
+                                              )
 {
+    TQ_T0();
     uint32_t acc[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) acc[i] = 0u;
@@ -225,7 +242,9 @@ __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *
             const int s = u % kStages;
             const uint4 a = ws.ring[s][0][lane], b = ws.ring[s][1][lane];
             const uint4 c = ws.ring[s][2][lane], d = ws.ring[s][3][lane];
-            if (kSubsample) {
+            if (kSubsample && (debug & 4u)) {
+                MA[0] |= a.x; MB[0] |= b.y; MC[0] |= c.z; MD[0] |= d.w;
+            } else if (kSubsample) {
                 const uint32_t valid = (a.x | a.y | a.z | a.w) & (b.x | b.y | b.z | b.w) &
                                        (c.x | c.y | c.z | c.w) & (d.x | d.y | d.z | d.w);
                 const uint32_t same = (a.x & b.x & c.x & d.x) | (a.y & b.y & c.y & d.y) |
@@ -245,22 +264,28 @@ __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *
                 if (++pending == kFlushEvery) { flush_acc(acc, ws.T, lane); pending = 0; }
             }
         }
-        if (kSubsample) {
+        TQ_ACC(0);
+        if (kSubsample && !(debug & 2u)) {
             count_tile(MA, MB, MC, MD, upper, acc);
             if (++pending == kFlushEvery) { flush_acc(acc, ws.T, lane); pending = 0; }
         }
+        TQ_ACC(1);
     }
     cp_async_wait<0>();
     flush_acc(acc, ws.T, lane);
+    TQ_ACC(2);
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: scores.  One-sided (Hestenes) Jacobi on the three 16x16 flattenings with fast scaled
-// rotations: the true column i is dsc[i] * M[.][i][.]; a rotation by tangent t of the true pair
-// (X, Y) -> (c (X - t Y), c (Y + t X)) only touches the stored columns with two FMAs per row
-// and multiplies both scales by c.  Lane (m, s) = (lane / 8, lane % 8) handles pair s of
-// matrix m in each of the 15 rounds of a round-robin sweep.  The tangent is computed in FP32
-// (a slightly-off angle only slows convergence); c = rsqrt(1 + t^2) and its inverse in FP64.
+// K4: scores.  One-sided (Hestenes) Jacobi on the three 16x16 flattenings, columns held in
+// REGISTERS.  Lane (m, s) = (lane / 8, lane % 8) owns two columns P and Q of matrix m (lanes
+// 24-31 idle on zero columns).  A sweep is a recursive-halving tournament of 8 + 4 + 2 + 1 = 15
+// steps that meets every pair of the 16 columns once: inside a group of g lanes the Q columns
+// circulate by one lane per step (34 warp shuffles), and between phases the lower half of each
+// group trades its Q for its partner's P through a small shared-memory buffer.  Shared-memory
+// traffic per step is ~4x lower than keeping the matrices in shared memory, which is what bounded
+// the first versions of this kernel (profiles/).  The rotation tangent uses approximate
+// reciprocal / rsqrt (a slightly-off angle only slows convergence); cos is refined to full FP64.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 {
@@ -273,12 +298,54 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 static constexpr double kTau2 = 1e-18;    // rotate when gamma^2 > tau^2 * |x|^2 |y|^2  (tau = 1e-9)
 static constexpr double kStop2 = 1e-8;    // a sweep whose largest relative gamma was < 1e-4 is the last
 
+__device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], double &nP, double &nQ,
+                                              double tiny, bool &big, bool force = false)
+{
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 16; r += 4) {
+        g0 = fma(P[r], Q[r], g0); g1 = fma(P[r + 1], Q[r + 1], g1);
+        g2 = fma(P[r + 2], Q[r + 2], g2); g3 = fma(P[r + 3], Q[r + 3], g3);
+    }
+    const double ga = (g0 + g1) + (g2 + g3);
+    const double ab = nP * nQ, gg = ga * ga;
+    if (force || (nP > tiny && nQ > tiny && gg > kTau2 * ab)) {
+        big |= gg > kStop2 * ab;
+        // Rotation that zeroes gamma:  with a = |Q|^2 - |P|^2, b = 2 gamma, r = sqrt(a^2 + b^2):
+        //   cos^2 = (1 + |a| / r) / 2,   sin = sign(a) * b / (2 r cos),   tan = sin / cos.
+        // Only two special-function ops (approximate FP64 rsqrt) sit on the dependency chain; the
+        // pair (cos, sin) is then renormalised so that cos^2 + sin^2 = 1 to FP64 accuracy (the
+        // angle itself may be ~1e-6 off, which only slows convergence).
+        const double a = nQ - nP, b2 = ga + ga;
+        const double q = fma(a, a, b2 * b2);
+        double ir;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ir) : "d"(q));       // ~ 1 / r
+        const double c2 = fma(0.5 * fabs(a), ir, 0.5);                   // cos^2 in [0.5, 1]
+        double rc;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(c2));      // ~ 1 / cos
+        double cs = c2 * rc;
+        double sn = (a < 0.0 ? -0.5 : 0.5) * b2 * ir * rc;
+        const double e = fma(cs, cs, fma(sn, sn, -1.0));                 // cos^2 + sin^2 - 1, ~1e-6
+        const double f = fma(e, fma(0.375, e, -0.5), 1.0);               // (1 + e)^(-1/2) to O(e^3)
+        cs *= f;
+        sn *= f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const double p = P[r], qq = Q[r];
+            P[r] = fma(cs, p, -(sn * qq));
+            Q[r] = fma(sn, p, cs * qq);
+        }
+        const double t = sn * rc;                                        // tan ~ sin / cos (only feeds the cached norms)
+        const double tg = t * ga;
+        nP -= tg;
+        nQ += tg;
+    }
+}
+
 __device__ __noinline__ void svd_scores(WarpScratch &ws, int lane, double *score_out, uint32_t *best_out,
-                                        uint32_t *minrank_out)
+                                        uint32_t *minrank_out, uint32_t debug)
 {
     auto &sv = ws.svd;
-    // T -> registers first: the SVD scratch overlays the cp.async ring, not T, but M is filled
-    // from every lane's 8 entries, so read them all before anyone writes
     double v[8];
     double fro2 = 0.0;
 #pragma unroll
@@ -299,95 +366,81 @@ __device__ __noinline__ void svd_scores(WarpScratch &ws, int lane, double *score
         sv.M[1][4 * b + d][4 * a + c] = v[i];       // rows (a,c), cols (b,d)
         sv.M[2][4 * b + c][4 * a + d] = v[i];       // rows (a,d), cols (b,c)
     }
-    for (int c = lane; c < 48; c += 32) { (&sv.dsc[0][0])[c] = 1.0; (&sv.esc[0][0])[c] = 1.0; }
     __syncwarp();
 
     const int m = lane >> 3, s = lane & 7;
-    const bool active = lane < 24;
-    double *const Mm = &sv.M[active ? m : 0][0][0];          // columns of this lane's matrix
-    double *const nrm = &sv.nrm[active ? m : 0][0];
-    double *const dsc = &sv.dsc[active ? m : 0][0];
-    double *const esc = &sv.esc[active ? m : 0][0];
+    double P[16], Q[16];
+    if (lane < 24) {
+        const double2 *cp = reinterpret_cast<const double2 *>(&sv.M[m][s][0]);
+        const double2 *cq = reinterpret_cast<const double2 *>(&sv.M[m][s + 8][0]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const double2 x = cp[r], y = cq[r];
+            P[2 * r] = x.x; P[2 * r + 1] = x.y; Q[2 * r] = y.x; Q[2 * r + 1] = y.y;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { P[r] = 0.0; Q[r] = 0.0; }
+    }
+    __syncwarp();                                    // M is free from here on: reuse it as xbuf
+    double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][9 double2] (144 B stride)
+
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
-        // refresh the cached norms from the columns
-        for (int c = lane; c < 48; c += 32) {
-            const double2 *col = reinterpret_cast<const double2 *>(&sv.M[c >> 4][c & 15][0]);
-            double n0 = 0.0, n1 = 0.0;
+        double nP = 0.0, nQ = 0.0;                   // refresh the cached squared norms
 #pragma unroll
-            for (int r = 0; r < 8; ++r) { const double2 x = col[r]; n0 = fma(x.x, x.x, n0); n1 = fma(x.y, x.y, n1); }
-            const double dd = (&sv.dsc[0][0])[c];
-            (&sv.nrm[0][0])[c] = (n0 + n1) * dd * dd;
-        }
-        __syncwarp();
+        for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
         bool big = false;
-        // round-robin pairing of 16 columns: slot 0 holds (15, rnd); slot s holds
-        // ((rnd + s) mod 15, (rnd - s) mod 15); i and j advance by one (mod 15) per round
-        int i = (s == 0) ? 15 : s, j = (s == 0) ? 0 : 15 - s;
-        for (int rnd = 0; rnd < 15; ++rnd) {
-            if (active) {
-                const double al = nrm[i], be = nrm[j];
-                double2 *ci = reinterpret_cast<double2 *>(Mm + i * kLdm);
-                double2 *cj = reinterpret_cast<double2 *>(Mm + j * kLdm);
-                double2 x[8], y[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) { x[r] = ci[r]; y[r] = cj[r]; }
-                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+        for (int g = 8; g >= 1; g >>= 1) {
+            for (int r = 0; r < g; ++r) {
+                jacobi_rotate(P, Q, nP, nQ, tiny, big, (debug & 64u) != 0);
+                if (r + 1 < g && !(debug & 16u)) {   // Q moves one lane down inside its group of g
+                    const int src = (lane & ~(g - 1)) | ((lane + 1) & (g - 1));
 #pragma unroll
-                for (int r = 0; r < 8; r += 2) {
-                    g0 = fma(x[r].x, y[r].x, g0); g1 = fma(x[r].y, y[r].y, g1);
-                    g2 = fma(x[r + 1].x, y[r + 1].x, g2); g3 = fma(x[r + 1].y, y[r + 1].y, g3);
+                    for (int k = 0; k < 16; ++k) Q[k] = __shfl_sync(kFull, Q[k], src);
+                    nQ = __shfl_sync(kFull, nQ, src);
                 }
-                const double di = dsc[i], dj = dsc[j];
-                const double ga = ((g0 + g1) + (g2 + g3)) * (di * dj);
-                const double ab = al * be, gg = ga * ga;
-                const bool rot = al > tiny && be > tiny && gg > kTau2 * ab;
-                if (rot) {
-                    big |= gg > kStop2 * ab;
-                    // tangent t = sign(z) / (|z| + sqrt(1 + z^2)), z = (be - al) / (2 ga): approximate
-                    // arithmetic is enough (a slightly-off angle only slows convergence)
-                    double inv2g;
-                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv2g) : "d"(ga + ga));
-                    const double z = (be - al) * inv2g;
-                    const float az = fminf(fabsf((float)z), 1e18f);
-                    const float w1 = fmaf(az, az, 1.0f);
-                    const float tf = __fdividef(1.0f, az + w1 * rsqrtf(w1));
-                    const double t = (z < 0.0) ? -(double)tf : (double)tf;
-                    // c = 1 / sqrt(1 + t^2) to full precision: approximate rsqrt + 2 Newton steps
-                    const double w = fma(t, t, 1.0);
-                    double cs;
-                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(cs) : "d"(w));
-                    cs = cs * fma(-0.5 * w, cs * cs, 1.5);
-                    cs = cs * fma(-0.5 * w, cs * cs, 1.5);
-                    const double ei = esc[i], ej = esc[j];
-                    const double rx = -(t * dj) * ei, ry = (t * di) * ej;
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        double2 nx, ny;
-                        nx.x = fma(rx, y[r].x, x[r].x); nx.y = fma(rx, y[r].y, x[r].y);
-                        ny.x = fma(ry, x[r].x, y[r].x); ny.y = fma(ry, x[r].y, y[r].y);
-                        ci[r] = nx; cj[r] = ny;
-                    }
-                    const double sec = w * cs;                         // 1 / cos
-                    const double tg = t * ga;
-                    dsc[i] = di * cs; dsc[j] = dj * cs;
-                    esc[i] = ei * sec; esc[j] = ej * sec;
-                    nrm[i] = al - tg; nrm[j] = be + tg;
-                }
-                if (s != 0) i = (i == 14) ? 0 : i + 1;
-                j = (j == 14) ? 0 : j + 1;
             }
-            __syncwarp();
+            if (g > 1 && !(debug & 16u)) {
+                // split every group in two: lower lanes keep P and take the partner's P as Q,
+                // upper lanes keep Q and take the partner's Q as P
+                const int h = g >> 1;
+                const bool lower = (lane & (g - 1)) < h;
+                double2 *mine = xbuf + lane * 9;
+                if (lower) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) mine[k] = make_double2(Q[2 * k], Q[2 * k + 1]);
+                    mine[8] = make_double2(nQ, 0.0);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) mine[k] = make_double2(P[2 * k], P[2 * k + 1]);
+                    mine[8] = make_double2(nP, 0.0);
+                }
+                __syncwarp();
+                const double2 *theirs = xbuf + (lower ? lane + h : lane - h) * 9;
+                if (lower) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const double2 x = theirs[k]; Q[2 * k] = x.x; Q[2 * k + 1] = x.y; }
+                    nQ = theirs[8].x;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { const double2 x = theirs[k]; P[2 * k] = x.x; P[2 * k + 1] = x.y; }
+                    nP = theirs[8].x;
+                }
+                __syncwarp();
+            }
         }
+        if (debug & 32u) { if (sweep == 8) break; else continue; }
         if (!__any_sync(kFull, big)) break;
     }
 
-    // singular values = true column norms; sort descending per matrix by rank counting
-    for (int c = lane; c < 48; c += 32) {
-        const double *col = &sv.M[c >> 4][c & 15][0];
-        double n2 = 0.0;
+    // singular values = column norms; sort descending per matrix by rank counting
+    {
+        double nP = 0.0, nQ = 0.0;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) n2 = fma(col[r], col[r], n2);
-        (&sv.nrm[0][0])[c] = sqrt(n2) * (&sv.dsc[0][0])[c];
+        for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
+        __syncwarp();
+        if (lane < 24) { sv.nrm[m][s] = sqrt(nP); sv.nrm[m][s + 8] = sqrt(nQ); }
     }
     __syncwarp();
     for (int c = lane; c < 48; c += 32) {
@@ -433,18 +486,33 @@ __device__ __noinline__ void svd_scores(WarpScratch &ws, int lane, double *score
 // consecutive quartets (neighbours in lexicographic order share tips -> L1 hits)
 // ------------------------------------------------------------------------------------------
 template <bool kSubsample>
-__global__ void __launch_bounds__(kWarps * 32, 4)
+__global__ void __launch_bounds__(kWarps * 32, TQ_MIN_CTAS)
 resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
                const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
                double *__restrict__ rscor, uint2 *__restrict__ rstat,
                uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
-               uint32_t *__restrict__ status)
+               uint32_t *__restrict__ status, uint32_t debug, uint32_t num_sms, uint32_t stagger_clk)
 {
-    __shared__ WarpScratch scratch[kWarps];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     WarpScratch &ws = scratch[warp];
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+#ifdef TQ_PHASE_TIMERS
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tq_start = clock64();
+#endif
+
+    // Every quartet costs the same, so co-resident warps would run their count and SVD phases in
+    // lock-step and leave the POPC pipe idle during the SVD phases.  Delay the k-th resident CTA of
+    // an SM by k quarter-periods once, at start: afterwards one warp per scheduler is in its SVD
+    // while the other three count.
+    if (stagger_clk) {
+        const uint32_t k = (blockIdx.x / num_sms) & 3u;
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)k * stagger_clk) __nanosleep(2000);
+    }
 
     for (int64_t q = (int64_t)blockIdx.x * kWarps + warp; q < m; q += nwarps) {
         const uint4 t = __ldg(quartets + q);
@@ -459,7 +527,12 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
 #pragma unroll
         for (int i = 0; i < 8; ++i) ws.T[lane + 32 * i] = 0u;
         __syncwarp();
-        count_quartet<kSubsample>(plan, planes, t, ws, lane);
+#ifdef TQ_PHASE_TIMERS
+        count_quartet<kSubsample>(plan, planes, t, ws, lane, debug, ph);
+        long long tq_t0 = clock64();
+#else
+        count_quartet<kSubsample>(plan, planes, t, ws, lane, debug);
+#endif
         __syncwarp();
         if (!kSubsample && lane < 4) ws.T[85u * lane] = 0u;   // invariant patterns aaaa, :218
         __syncwarp();
@@ -474,14 +547,15 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
 
         double score[3] = {0.001, 0.001, 0.001};                        // :232
         uint32_t best, minrank = 0;
-        if (nsnps == 0) {
+        if (nsnps == 0 || (debug & 1u)) {
             uint64_t h = seed;
             h = splitmix64(h ^ t.x); h = splitmix64(h ^ t.y);
             h = splitmix64(h ^ t.z); h = splitmix64(h ^ t.w);
             best = (uint32_t)(h % 3ull);                                // stands in for :231
         } else {
-            svd_scores(ws, lane, score, &best, &minrank);
+            svd_scores(ws, lane, score, &best, &minrank, debug);
         }
+        TQ_ACC(3);
         if (lane == 0) {
             rscor[3 * q] = score[0]; rscor[3 * q + 1] = score[1]; rscor[3 * q + 2] = score[2];
             rstat[q] = make_uint2(best, nsnps);                         // :251, :264
@@ -489,6 +563,13 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
         }
         __syncwarp();
     }
+#ifdef TQ_PHASE_TIMERS
+    if (lane == 0) {
+        for (int i = 0; i < 4; ++i) atomicAdd(&g_phase_clk[i], (unsigned long long)ph[i]);
+        atomicAdd(&g_phase_clk[4], (unsigned long long)(clock64() - tq_start));
+        atomicAdd(&g_phase_clk[5], 1ull);
+    }
+#endif
 }
 
 cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips,
@@ -498,21 +579,47 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
                            cudaStream_t stream)
 {
     if (m == 0) return cudaSuccess;
+    static const uint32_t debug = getenv("TQ_DEBUG") ? (uint32_t)atoi(getenv("TQ_DEBUG")) : 0u;   // phase knock-outs for profiling only
     const int64_t want = (m + kWarps - 1) / kWarps;
-    const int64_t cap = (int64_t)num_sms * 4;          // 4 resident CTAs per SM (launch bounds)
+    // quarter of the estimated per-quartet period of a warp (clocks): 4 warps share one POPC pipe
+    // (256 POPC x ~8.5 clk per tile each) plus ~100k clocks of SVD; only worth it with >= 8 quartets/warp
+    uint32_t stagger = 0;
+    if (m >= (int64_t)num_sms * 16 * 8 && !(debug & 8u))
+        stagger = (uint32_t)(((int64_t)plan.ntiles * 10200 + 120000) / 4);
+    if (getenv("TQ_STAGGER")) stagger = (uint32_t)atoi(getenv("TQ_STAGGER"));
+    const int64_t cap = (int64_t)num_sms * TQ_MIN_CTAS;   // resident CTAs per SM (launch bounds)
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     const uint4 *planes = reinterpret_cast<const uint4 *>(d_planes);
     const uint4 *quartets = reinterpret_cast<const uint4 *>(d_quartets);
     uint2 *rstat = reinterpret_cast<uint2 *>(d_rstat);
+    const size_t smem = sizeof(WarpScratch) * kWarps;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
     if (subsample)
-        resolve_kernel<true><<<grid, kWarps * 32, 0, stream>>>(plan, planes, (uint32_t)ntips, quartets,
+        resolve_kernel<true><<<grid, kWarps * 32, smem, stream>>>(plan, planes, (uint32_t)ntips, quartets,
                                                                m, seed, d_rscor, rstat, d_counts,
-                                                               d_minrank, d_status);
+                                                               d_minrank, d_status, debug, (uint32_t)num_sms, stagger);
     else
-        resolve_kernel<false><<<grid, kWarps * 32, 0, stream>>>(plan, planes, (uint32_t)ntips, quartets,
+        resolve_kernel<false><<<grid, kWarps * 32, smem, stream>>>(plan, planes, (uint32_t)ntips, quartets,
                                                                 m, seed, d_rscor, rstat, d_counts,
-                                                                d_minrank, d_status);
+                                                                d_minrank, d_status, debug, (uint32_t)num_sms, stagger);
     ++g_launches;
+#ifdef TQ_PHASE_TIMERS
+    {
+        cudaDeviceSynchronize();
+        unsigned long long h[8];
+        cudaMemcpyFromSymbol(h, g_phase_clk, sizeof(h));
+        const double w = (double)h[5];
+        fprintf(stderr, "[phase clk per warp] stage1 %.0f stage2 %.0f flush %.0f svd+out %.0f total %.0f (warps %.0f)\n",
+                h[0] / w, h[1] / w, h[2] / w, h[3] / w, h[4] / w, w);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
+    }
+#endif
     return cudaGetLastError();
 }
 
