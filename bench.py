@@ -168,7 +168,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import tetrad_b200
-    from tetrad_b200 import _lib
+    from tetrad_b200 import _lib, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -180,6 +180,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -202,7 +204,7 @@ def run_ours(args):
         rstat, rscor = eng.resolve(qd, True)
         ev[3].record(stream)
         if world > 1:
-            packed = torch.cat([rscor, rstat.view(torch.float64)], dim=1)   # 32 B / quartet
+            packed = sharding.pack_results(rstat, rscor)                     # 32 B / quartet
             dist.gather(packed, gather_buf, dst=0)
         ev[1].record(stream)
         return ev, (rstat, rscor)

@@ -147,6 +147,32 @@ def main():
     unr200 = np.array([_index_to_combination(int(i), 200) for i in big], dtype=np.uint32)
     np.savez_compressed(GOLD / "unrank.npz", idx12=idx, comb12=unr12, idx200=big, comb200=unr200)
 
+    # (8) result sink + wQMC formatting: the reference's own pandas line (run_inference.py:232-234)
+    #     and iter_qmc_formatted (:254-305), executed on the noisy12 results
+    import types as _types
+    for mod in ("ipyparallel", "toytree"):
+        sys.modules.setdefault(mod, _types.ModuleType(mod))
+    sys.modules["ipyparallel"].Client = object
+    clus = _types.ModuleType("tetrad.src.cluster"); clus.Cluster = object
+    sys.modules["tetrad.src.cluster"] = clus
+    import pandas as pd
+    from tetrad.src import run_inference as ref_run
+    import tempfile
+    g = np.load(GOLD / "noisy12.npz")
+    rqrts, rstat, rscor = g["quartets"], g["sub_rstat"], g["sub_rscor"]
+    tabular = pd.concat([pd.DataFrame(i) for i in (rqrts, rscor, rstat)], axis=1)
+    tsv = tabular.to_csv(sep="\t", float_format='%.6f', index=False, header=False)
+    qmc = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        f = Path(tmp) / "q.tsv"
+        f.write_text(tsv)
+        for weights in (0, 1, 2, 3):
+            qmc[f"w{weights}"] = "\n".join(ref_run.iter_qmc_formatted(f, weights))
+        qmc["w1_minsnps400"] = "\n".join(ref_run.iter_qmc_formatted(f, 1, min_snps=400))
+        qmc["w2_minratio5"] = "\n".join(ref_run.iter_qmc_formatted(f, 2, min_ratio=5.0))
+    np.savez_compressed(GOLD / "sink.npz", tsv=np.array(tsv), **{k: np.array(v) for k, v in qmc.items()})
+    print("sink:", len(tsv.splitlines()), "tsv lines;", {k: len(v.splitlines()) for k, v in qmc.items()})
+
     (GOLD / "VERSIONS.txt").write_text(
         "golden vectors generated by oracle/gen_golden.py executing /root/reference with\n"
         + "\n".join(f"{k}={v}" for k, v in versions.items()) + "\n")

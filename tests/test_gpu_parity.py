@@ -168,3 +168,33 @@ def test_size_independent_properties_at_bench_shape(tb):
     # idempotence
     rstat2, rscor2 = eng.resolve(quartets, True)
     assert (rstat2 == rstat).all() and (rscor2 == rscor).all()
+
+
+def test_tetrad_facade_and_cli_end_to_end(tb, oracle, tmp_path):
+    """Tetrad(name, data, nquartets, nboots).run() and `tetrad init` + `tetrad run`: TSV rows equal
+    the oracle's resolution of the same replicate arrays."""
+    from tetrad_b200 import cli, database, run_inference, synth
+    from tetrad_b200.schema import Project
+    d = synth.generate(8, 300, 1200, seed=21)
+    database.write_snps_input(tmp_path / "in.npz", d.snps, d.snpsmap, d.names)
+    tet = tb.Tetrad("fac", str(tmp_path / "in.npz"), workdir=str(tmp_path / "w"), nquartets=0, nboots=1, seed=7)
+    tet.run()
+    proj = Project.load_json(tmp_path / "w" / "fac.json")
+    assert proj.bootstrap_idx == 2 and proj.nqrts == 70
+    q, scores, best, nsnps = run_inference.read_quartets_tsv(tmp_path / "w" / "fac.quartets_0.tsv")
+    arrays = database.read_arrays(proj.database_file, ["tmparr", "tmpmap"])
+    _, ostat, oscor = oracle.new_infer_resolved_quartets(arrays["tmparr"], arrays["tmpmap"], q.astype(np.uint32), True)
+    assert (nsnps == ostat[:, 1]).all() and (best == ostat[:, 0]).all()
+    np.testing.assert_allclose(scores, oscor, rtol=1e-5, atol=1e-6)      # TSV carries 6 decimals
+    assert (tmp_path / "w" / "fac.quartets_1.tsv").exists() and (tmp_path / "w" / "fac.qmc_in.txt").exists()
+    # CLI: init + run (full mode: the live CLI's default is subsample_snps=False)
+    assert cli.main(["init", str(tmp_path / "in.npz"), "-n", "c", "-w", str(tmp_path / "c"), "-r", "3"]) == 0
+    assert cli.main(["run", str(tmp_path / "c" / "c.json"), "-c", "4", "-b", "0"]) == 0
+    q, scores, best, nsnps = run_inference.read_quartets_tsv(tmp_path / "c" / "c.quartets_0.tsv")
+    cproj = Project.load_json(tmp_path / "c" / "c.json")
+    arrays = database.read_arrays(cproj.database_file, ["tmparr", "tmpmap"])
+    _, ostat, _ = oracle.new_infer_resolved_quartets(arrays["tmparr"], arrays["tmpmap"], q.astype(np.uint32), False)
+    assert cproj.subsample_snps is False and (nsnps == ostat[:, 1]).all() and (best == ostat[:, 0]).all()
+    # engine entry point with the reference's signature
+    rq, rstat, rscor = tb.infer_resolved_quartets(cproj.database_file, 8, [(0, 1, 2, 3), (1, 3, 5, 7)], False)
+    assert rstat.shape == (2, 2) and rscor.shape == (2, 3) and rq.shape == (2, 4)

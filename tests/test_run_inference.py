@@ -1,0 +1,131 @@
+"""CPU: the caller side of the hot path -- result sink, wQMC formatting, resampling, project
+files, replicate loop -- against golden text produced by the executed reference."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from tetrad_b200 import combinations, database, run_inference, synth, write_database
+from tetrad_b200.schema import Project, RNGStateModel
+
+
+def test_tsv_matches_reference_pandas_output(tmp_path):
+    g, sink = load_golden("noisy12"), load_golden("sink")
+    f = tmp_path / "q.tsv"
+    run_inference.write_quartets_tsv(f, g["quartets"], g["sub_rstat"], g["sub_rscor"])
+    assert f.read_text() == str(sink["tsv"])
+
+
+@pytest.mark.parametrize("key,kwargs", [("w0", dict(weights=0)), ("w1", dict(weights=1)), ("w2", dict(weights=2)),
+                                        ("w3", dict(weights=3)), ("w1_minsnps400", dict(weights=1, min_snps=400)),
+                                        ("w2_minratio5", dict(weights=2, min_ratio=5.0))])
+def test_qmc_format_matches_reference(tmp_path, key, kwargs):
+    sink = load_golden("sink")
+    f = tmp_path / "q.tsv"
+    f.write_text(str(sink["tsv"]))
+    assert "\n".join(run_inference.iter_qmc_formatted(f, **kwargs)) == str(sink[key])
+
+
+def test_write_qmc_format_is_a_seeded_permutation(tmp_path):
+    sink = load_golden("sink")
+    f = tmp_path / "q.tsv"
+    f.write_text(str(sink["tsv"]))
+    n = run_inference.write_qmc_format(f, tmp_path / "a.txt", 1, rng=3)
+    run_inference.write_qmc_format(f, tmp_path / "b.txt", 1, rng=3)
+    a = (tmp_path / "a.txt").read_text()
+    assert a == (tmp_path / "b.txt").read_text() and n == 495
+    assert sorted(a.splitlines()) == sorted(str(sink["w1"]).splitlines())
+    assert a.splitlines() != str(sink["w1"]).splitlines()
+
+
+def test_relabel_tree():
+    names = {0: "a", 1: "b_1", 2: "c", 3: "d", 10: "k"}
+    assert run_inference.relabel_tree("((0,1),(2,(3,10)));\n", names) == "((a,b_1),(c,(d,k)));"
+    assert run_inference.relabel_tree("((0:1,1:1):2,(2,3));", names) == "((a:1,b_1:1):2,(c,d));"
+
+
+def test_resample_arrays_semantics_and_rng_stream():
+    d = synth.generate(6, 40, 150, seed=3, p_ambig=0.0)
+    db = synth.prepare_database(d.snps, d.snpsmap, seed=1)
+    rng = np.random.default_rng(11)
+    tmparr, tmpmap = run_inference.resample_arrays(db["seqarr"], db["spans"], rng)
+    # the main stream advanced by exactly the reference's three draws (run_inference.py:117-123)
+    ref = np.random.default_rng(11)
+    lidxs = ref.choice(40, 40, replace=True); ref.integers(2**31); ref.integers(2**31)
+    assert rng.integers(1 << 30) == ref.integers(1 << 30)
+    lens = db["spans"][lidxs, 1] - db["spans"][lidxs, 0]
+    assert tmparr.shape[1] == lens.sum() and (np.bincount(tmpmap[:, 0], minlength=40) == lens).all()
+    assert (tmpmap[:, 1] == np.arange(tmparr.shape[1])).all()
+    assert set(np.unique(tmparr)) <= {0, 1, 2, 3, 78}
+    # every instance is a column permutation of its source locus (no ambiguity codes in this data set)
+    recoded = synth.recode_acgt(db["seqarr"].copy())
+    off, moved = 0, 0
+    for l in lidxs:
+        a, b = db["spans"][l]
+        src, got = recoded[:, a:b], tmparr[:, off: off + (b - a)]
+        off += b - a
+        assert sorted(map(bytes, src.T)) == sorted(map(bytes, got.T))
+        moved += int((src != got).any())
+    assert moved > 0                      # and the order really is shuffled
+
+
+def test_project_json_roundtrip_and_names(tmp_path):
+    proj = Project(version="0.1.0", data=tmp_path / "in.npz", name="T", workdir=tmp_path / "w", subsample_snps=True,
+                   weights=1, nquartets=0, random_seed=5)
+    assert proj.qrts_file.name == "T.quartets_0.tsv" and proj.database_file.name == "T.database.hdf5"
+    assert proj.best_file.name == "T.best_tree.nwk" and proj.boots_file.name == "T.boots.nwk"
+    assert proj.qmc_in_file.name == "T.qmc_in.txt" and proj.json_file.name == "T.json"
+    rng = np.random.default_rng(1); rng.random(3)
+    proj.bootstrap_rng = RNGStateModel.from_rng(rng)
+    proj.samples = {0: "a", 1: "b"}
+    proj.save_json()
+    back = Project.load_json(proj.json_file)
+    assert back.samples == {0: "a", 1: "b"} and back.bootstrap_rng.to_rng().random() == rng.random()
+    fields = json.loads(proj.json_file.read_text())
+    for key in ("version", "data", "name", "workdir", "subsample_snps", "weights", "nquartets", "random_seed",
+                "bootstrap_idx", "bootstrap_rng", "nsnps", "nsamples", "nqrts", "nqrts_total", "samples"):
+        assert key in fields
+
+
+def test_get_nquartets_follows_reference_rules():
+    assert write_database.get_nquartets(12, 0) == (495, 495)
+    assert write_database.get_nquartets(12, 10**6) == (495, 495)
+    assert write_database.get_nquartets(50, 100) == (100, 230300)          # low: warn, keep
+    assert write_database.get_nquartets(50, 100000) == (100000, 230300)
+
+
+class _OracleEngine:
+    """stands in for QuartetResolver on the CPU box (tests only)"""
+    def load(self, tmparr, tmpmap):
+        self.tmparr, self.tmpmap = tmparr, tmpmap
+    def resolve(self, quartets, subsample):
+        import torch
+        from oracle import oracle
+        _, rstat, rscor = oracle.new_infer_resolved_quartets(self.tmparr, self.tmpmap, quartets.numpy().view(np.uint32), subsample)
+        return torch.from_numpy(rstat.view(np.int32)), torch.from_numpy(rscor)
+
+
+def test_replicate_loop_checkpoints_and_resumes(tmp_path, oracle):
+    d = synth.generate(7, 60, 240, seed=8)
+    database.write_snps_input(tmp_path / "in.npz", d.snps, d.snpsmap, d.names)
+    proj = Project(version="0.1.0", data=tmp_path / "in.npz", name="R", workdir=tmp_path, subsample_snps=True,
+                   weights=1, nquartets=0, random_seed=42)
+    write_database.write_database(proj)
+    assert (proj.nsamples, proj.nsnps, proj.nqrts, proj.nqrts_total) == (7, 240, 35, 35)
+    proj.save_json()
+    run_inference.run_inference(proj, nboots=1, resolver=_OracleEngine())
+    assert proj.bootstrap_idx == 2
+    t0 = (tmp_path / "R.quartets_0.tsv").read_text().splitlines()
+    t1 = (tmp_path / "R.quartets_1.tsv").read_text().splitlines()
+    assert len(t0) == 35 and len(t1) == 35 and t0 != t1 and len(t0[0].split("\t")) == 9
+    assert (tmp_path / "R.qmc_in.txt").exists()
+    # resume from the JSON checkpoint: replicate 2 must equal a straight 0..2 run
+    again = Project.load_json(proj.json_file)
+    run_inference.run_inference(again, nboots=2, resolver=_OracleEngine())
+    fresh = Project(version="0.1.0", data=tmp_path / "in.npz", name="S", workdir=tmp_path, subsample_snps=True,
+                    weights=1, nquartets=0, random_seed=42)
+    write_database.write_database(fresh)
+    run_inference.run_inference(fresh, nboots=2, resolver=_OracleEngine())
+    assert (tmp_path / "R.quartets_2.tsv").read_text() == (tmp_path / "S.quartets_2.tsv").read_text()

@@ -5,8 +5,9 @@ hand-written sm_100a CUDA behind a C ABI (``include/tetrad_b200.h``); see DESIGN
 """
 __version__ = "0.1.0"
 
-from .resolve_quartets import (  # noqa: F401
+from .resolve_quartets import (  # noqa: F401,E402
     QuartetResolver,
     infer_resolved_quartets,
     new_infer_resolved_quartets,
 )
+from .tetrad import Tetrad  # noqa: F401,E402

@@ -103,15 +103,11 @@ def last_traffic(device: int = 0) -> tuple[int, int]:
 
 
 def load_database(database: Path):
-    """``tmparr``, ``tmpmap`` of a working database (reference :33-35).  ``.npz`` files are read
-    with numpy; HDF5 files with the bundled reader (``tetrad_b200.hdf5``)."""
-    database = Path(database)
-    if database.suffix == ".npz":
-        with np.load(database) as io5:
-            return io5["tmparr"], io5["tmpmap"]
-    from . import hdf5
-    with hdf5.File(database, "r") as io5:
-        return io5["tmparr"][:], io5["tmpmap"][:]
+    """``tmparr``, ``tmpmap`` of a working database (reference :33-35); see ``database.py`` for
+    the container formats (numpy archive, or HDF5 via h5py / the bundled subset reader)."""
+    from . import database as dbio
+    arrays = dbio.read_arrays(Path(database), ["tmparr", "tmpmap"])
+    return arrays["tmparr"], arrays["tmpmap"]
 
 
 def infer_resolved_quartets(database: Path, nsamples: int, qrts: Iterable[tuple[int, int, int, int]],

@@ -1,0 +1,231 @@
+"""Replicate loop around the hot path: the caller side of ``infer_resolved_quartets``.
+
+Mirrors the reference's tetrad/src/run_inference.py: ``run_inference`` (:360-407),
+``resample_tmp_database`` (:99-143), the TSV sink of ``distributor`` (:232-247),
+``iter_qmc_formatted`` / ``write_qmc_format`` (:254-327), ``run_qmc`` (:146-166),
+``relabel_tree`` (:169-181), ``infer_supertree`` (:330-357).  The ipyparallel process farm is
+replaced by the GPU engine (``QuartetResolver``), optionally sharded over ranks
+(``tetrad_b200.sharding``); wQMC itself (a prebuilt binary the reference ships in ``bin/``) is
+invoked unchanged when it can be found, and skipped with a warning otherwise.
+
+The numpy ``Generator`` stream is consumed in the reference's order, so for a given
+``random_seed`` every replicate resolves the same quartet set and the same resampled loci as the
+reference would; only the within-locus shuffles and ambiguity coin-flips, which the reference
+draws from numba's private RNG, come from a different stream.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import re
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+from . import combinations, database, synth
+from .schema import Project, RNGStateModel
+
+logger = logging.getLogger("tetrad_b200")
+
+# split index -> tip order "a,b|c,d" (reference run_inference.py:41-45, 264-270)
+TIDXS = np.array([[0, 1, 2, 3], [0, 2, 1, 3], [0, 3, 1, 2]], dtype=np.uint8)
+
+
+# ----------------------------------------------------------------------------------------------
+# bootstrap resampling (reference :99-143)
+# ----------------------------------------------------------------------------------------------
+def resample_arrays(seqarr: np.ndarray, spans: np.ndarray, rng: np.random.Generator):
+    """One bootstrap replicate of (tmparr, tmpmap).  Draws from ``rng`` exactly what
+    ``resample_tmp_database`` draws (:117 loci with replacement, :120 and :123 two 31-bit
+    seeds); the two seeds feed the within-locus shuffle and the ambiguity resolution."""
+    nloci = spans.shape[0]
+    lidxs = rng.choice(nloci, nloci, replace=True)
+    seed_shuffle = int(rng.integers(2**31))
+    seed_ambig = int(rng.integers(2**31))
+    lens = (spans[lidxs, 1] - spans[lidxs, 0]).astype(np.int64)
+    total = int(lens.sum())
+    inst = np.repeat(np.arange(nloci, dtype=np.int64), lens)
+    sub = np.random.default_rng(seed_shuffle)
+    order = np.lexsort((sub.random(total), inst))          # random order inside every instance
+    first = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    cols = np.repeat(spans[lidxs, 0], lens) + (order - np.repeat(first, lens))
+    tmparr = np.ascontiguousarray(seqarr[:, cols])
+    tmpmap = np.zeros((total, 2), dtype=np.uint32)
+    tmpmap[:, 0] = inst                                     # resample.py:58
+    tmpmap[:, 1] = np.arange(total)
+    tmparr = synth.recode_acgt(synth.resolve_ambigs(tmparr, np.random.default_rng(seed_ambig)))
+    return tmparr, tmpmap
+
+
+# ----------------------------------------------------------------------------------------------
+# result sink (reference :232-247)
+# ----------------------------------------------------------------------------------------------
+def write_quartets_tsv(path: Path, quartets, rstat, rscor, append: bool = False) -> None:
+    """``t0 t1 t2 t3 s0 s1 s2 best nsnps``, tab-separated, scores ``%.6f``, no header: the line
+    format pandas produces at run_inference.py:232-234."""
+    table = np.empty((len(quartets), 9), dtype=np.float64)
+    table[:, 0:4] = quartets
+    table[:, 4:7] = rscor
+    table[:, 7:9] = rstat
+    with open(path, "a" if append else "w") as out:
+        np.savetxt(out, table, fmt="%d\t%d\t%d\t%d\t%.6f\t%.6f\t%.6f\t%d\t%d")
+
+
+def read_quartets_tsv(path: Path):
+    """(quartets i64[m,4], scores f64[m,3], best i64[m], nsnps i64[m]) parsed from the TSV."""
+    if os.path.getsize(path) == 0:
+        z = np.zeros((0, 9))
+    else:
+        z = np.loadtxt(path, delimiter="\t", ndmin=2)
+    return z[:, 0:4].astype(np.int64), z[:, 4:7], z[:, 7].astype(np.int64), z[:, 8].astype(np.int64)
+
+
+def iter_qmc_formatted(qrts_file: Path, weights: int, min_snps: int = 0, min_ratio: float = 1.0):
+    """Yield resolved quartets in wQMC format ``a,b|c,d:weight`` (reference :254-305), computed
+    from the TSV text like the reference does, but vectorised."""
+    if weights not in (0, 1, 2, 3):
+        raise ValueError(f"no weight strategy {weights}")
+    min_snps = max(1, min_snps)
+    quartets, scores, best, nsnps = read_quartets_tsv(qrts_file)
+    order = TIDXS[best]                                          # :264-270
+    tips = np.take_along_axis(quartets, order.astype(np.int64), axis=1)
+    srt = np.sort(scores, axis=1)                                # :281
+    if not weights:
+        weight = np.ones(len(quartets))
+        ratio = np.ones(len(quartets))
+    else:
+        smean = srt[:, 1:].mean(axis=1)                          # :282
+        smin = srt[:, 0]                                         # :283
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = np.where(smin == 0, 1.0, smean / np.where(smin == 0, 1.0, smin))   # :284
+            third = 1.0 - smin / srt.sum(axis=1)                 # :292
+        weight = {1: smean, 2: ratio, 3: third}[weights]
+    keep = (nsnps >= min_snps) & ~(ratio < min_ratio)            # :275, :300
+    for (a, b, c, d), w in zip(tips[keep].tolist(), weight[keep].tolist()):
+        yield "{},{}|{},{}:{:.5f}".format(a, b, c, d, w)
+
+
+def write_qmc_format(qrts_file: Path, qmc_in_file: Path, weights: int = 0, min_snps: int = 0,
+                     min_ratio: float = 1.0, rng=None) -> int:
+    """Write the weighted quartets in random order (reference :308-327; the reference shells out
+    to ``shuf``, which cannot be seeded -- here the order comes from ``rng``)."""
+    lines = list(iter_qmc_formatted(qrts_file, weights, min_snps, min_ratio))
+    perm = np.random.default_rng(rng).permutation(len(lines))
+    with open(qmc_in_file, "w") as out:
+        out.write("".join(lines[i] + "\n" for i in perm))
+    return len(lines)
+
+
+# ----------------------------------------------------------------------------------------------
+# supertree (reference :48-70, :146-181, :330-357)
+# ----------------------------------------------------------------------------------------------
+def get_qmc_bin():
+    """Path of the wQMC ``max-cut-tree`` binary, or None.  Search order: $TETRAD_QMC_BIN,
+    ``sys.prefix/bin`` (conda install, reference :56), ``PATH``."""
+    cands = [os.environ.get("TETRAD_QMC_BIN"), str(Path(sys.prefix) / "bin" / "max-cut-tree"),
+             shutil.which("max-cut-tree")]
+    for cand in cands:
+        if cand and Path(cand).exists():
+            return Path(cand)
+    return None
+
+
+def run_qmc(qmc_in_file: Path, qmc_out_file: Path, use_weights: bool) -> None:
+    """Run wQMC (reference :146-166)."""
+    qmc = get_qmc_bin()
+    if qmc is None:
+        raise IOError("No wQMC binary found (set TETRAD_QMC_BIN)")
+    cmd = [str(qmc), f"qrtt={qmc_in_file}", f"otre={qmc_out_file}", f"weights={'on' if use_weights else 'off'}"]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if proc.returncode:
+        raise RuntimeError(f"error in wQMC: {proc.stdout!r}")
+
+
+_TIP = re.compile(r"(?<=[(,])\s*(\d+)\s*(?=[:,)])")
+
+
+def relabel_tree(newick: str, samples: dict) -> str:
+    """Replace numeric tip labels by sample names (reference :169-181, without toytree)."""
+    newick = newick.strip()
+    return _TIP.sub(lambda m: str(samples[int(m.group(1))]), newick)
+
+
+def infer_supertree(proj: Project, idx: int, weights: int, min_snps: int = 0, min_ratio: float = 1.0,
+                    rng=None):
+    """Quartet supertree of replicate ``idx`` as newick, or None without a wQMC binary.  Unlike the
+    reference (:337-351) the tree that is relabelled is the one wQMC wrote for THIS replicate."""
+    qrts_file = proj.workdir / f"{proj.name}.quartets_{idx}.tsv"
+    if idx:
+        qmc_in = proj.qmc_in_file.parent / f"tmp_in{idx}"
+        qmc_out = proj.qmc_out_file.parent / f"tmp_out{idx}"
+    else:
+        qmc_in, qmc_out = proj.qmc_in_file, proj.qmc_out_file
+    write_qmc_format(qrts_file, qmc_in, weights, min_snps, min_ratio, rng=rng)
+    if get_qmc_bin() is None:
+        logger.warning("wQMC binary not found: quartets written, supertree skipped")
+        return None
+    run_qmc(qmc_in, qmc_out, bool(weights))
+    nwk = relabel_tree(Path(qmc_out).read_text(), proj.samples)
+    if idx:
+        qmc_in.unlink()
+        qmc_out.unlink()
+    return nwk
+
+
+# ----------------------------------------------------------------------------------------------
+# replicate loop (reference :360-407)
+# ----------------------------------------------------------------------------------------------
+def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int = 0, resolver=None) -> None:
+    """Resolve replicate 0 (original data) and ``nboots`` bootstrap replicates, checkpointing
+    after each one exactly like the reference (:405-407).  ``ncores`` is accepted for CLI
+    compatibility and ignored: the work runs on the GPU(s).  ``resolver`` (tests) overrides the
+    engine: any object with ``load(tmparr, tmpmap)`` and ``resolve(quartets, subsample)``."""
+    import torch
+    import torch.distributed as dist
+    from . import sharding
+
+    arrays = database.read_arrays(proj.database_file, ["seqarr", "spans", "tmparr", "tmpmap"])
+    if resolver is None:
+        from .resolve_quartets import QuartetResolver
+        resolver = QuartetResolver(device=device, seed=proj.random_seed or 0)
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+    if proj.bootstrap_rng is None:
+        logger.info("starting quartet tree inference")
+        rng = np.random.default_rng(proj.random_seed)
+    else:
+        logger.info("continuing quartet tree inference")
+        rng = proj.bootstrap_rng.to_rng()
+
+    full = combinations.all_quartets(proj.nsamples) if proj.nqrts == proj.nqrts_total else None
+    while proj.bootstrap_idx <= nboots:
+        # the reference's quartet generator is lazy: its draw happens after the resampling draws
+        if proj.bootstrap_idx:
+            tmparr, tmpmap = resample_arrays(arrays["seqarr"], arrays["spans"], rng)
+        else:
+            tmparr, tmpmap = arrays["tmparr"], arrays["tmpmap"]
+        quartets = full if full is not None else combinations.random_quartets(proj.nsamples, proj.nqrts, rng)
+
+        resolver.load(tmparr, tmpmap)
+        q_dev = torch.from_numpy(quartets.view(np.int32))
+        if hasattr(resolver, "device"):
+            q_dev = q_dev.to(resolver.device)
+        out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
+        if rank == 0:
+            rstat, rscor = out
+            write_quartets_tsv(proj.qrts_file, quartets, rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy())
+            nwk = infer_supertree(proj, proj.bootstrap_idx, proj.weights, rng=proj.bootstrap_idx)
+            if nwk is not None:
+                if proj.bootstrap_idx == 0:
+                    proj.best_file.write_text(nwk + "\n")
+                else:
+                    with open(proj.boots_file, "a") as outfh:
+                        outfh.write(nwk + "\n")
+        logger.info(f"finished rep {proj.bootstrap_idx}")
+        proj.bootstrap_idx += 1
+        proj.bootstrap_rng = RNGStateModel.from_rng(rng)
+        if rank == 0:
+            proj.save_json()
