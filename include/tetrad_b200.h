@@ -59,6 +59,9 @@ typedef struct tq_plan tq_plan;
 
 int  tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride,
                     int device, void *stream, tq_plan **out);
+/* Same plan from the run lengths alone (run i covers the next h_run_len[i] columns): used for
+ * bootstrap replicates, whose instance lengths are known before any column is materialised. */
+int  tq_plan_create_runs(const uint32_t *h_run_len, int64_t nruns, int device, void *stream, tq_plan **out);
 void tq_plan_destroy(tq_plan *plan);
 
 /* info[0]=ncols  [1]=nloci  [2]=ntiles  [3]=row_words (u32 words per tip row of the packed matrix)
@@ -67,9 +70,10 @@ int  tq_plan_info(const tq_plan *plan, int64_t info[8]);
 
 /* Copies of the plan's tables (any pointer may be NULL): tile_off u32[ntiles+1] (offset of each
  * tile inside a tip row, in 16-byte units), tile_k u32[ntiles] (ranks per tile), loc_start /
- * loc_len u32[ntiles*1024] (first column and length of each locus in sorted order, 0-padded). */
+ * loc_len u32[ntiles*1024] (first column and length of each locus in sorted order, 0-padded),
+ * loc_run u32[ntiles*1024] (index of that locus run in column order, before the length sort). */
 int  tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k,
-                    uint32_t *loc_start, uint32_t *loc_len);
+                    uint32_t *loc_start, uint32_t *loc_len, uint32_t *loc_run);
 
 /* ------------------------------------------------------------------------------------------
  * K1: pack.  d_tmparr u8[ntips][row_stride] (device)  ->  d_planes u32[ntips][row_words] (device):
@@ -79,6 +83,22 @@ int  tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k,
  */
 int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t row_stride,
             uint32_t *d_planes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2/K5: bootstrap replicate packed on the device.  Replaces resample_tmp_database + jit_resample +
+ * jit_resolve_ambigs (run_inference.py:99-143, tetrad/jit/resample.py:20-64,
+ * tetrad/jit/resolve_ambigs.py:12-36) for replicates >= 1: `plan` comes from
+ * tq_plan_create_runs(lengths of the drawn loci); d_src_start u32[nruns] is the first column, in
+ * d_seqarr, of the locus drawn for instance i (spans[lidxs[i], 0]); d_seqarr u8[ntips][row_stride]
+ * holds ASCII codes (A C G T, N / - = missing, R K S Y W M = two-base ambiguity) or codes 0..3.
+ * Inside every instance the column order is a Philox4x32-10 permutation keyed by seed_shuffle; every
+ * ambiguity cell takes one of its two bases by a Philox coin keyed by seed_ambig (the reference
+ * uses numba's private generator for both, so only the distribution can match -- SURVEY.md H6).
+ * d_srccol is caller-owned scratch of plan info[5] (padded columns) u32.
+ */
+int tq_boot_pack(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
+                 const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
+                 uint32_t *d_srccol, uint32_t *d_planes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3+K4: resolve.  For each of the m quartets in d_quartets u32[m][4]:

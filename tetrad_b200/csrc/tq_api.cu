@@ -46,7 +46,7 @@ struct tq_plan {
     int64_t ncols = 0, nloci = 0, ntiles = 0, row_u4 = 0, max_len = 0, padded_cols = 0;
     void *d_tables = nullptr;      // one allocation: tile_off | tile_k | loc_start | loc_len
     std::vector<uint32_t> h_tables; // host copy of the same tables
-    size_t o_off = 0, o_k = 0, o_start = 0, o_len = 0;
+    size_t o_off = 0, o_k = 0, o_start = 0, o_len = 0, o_run = 0;
     tq::PlanDev dev{};
 };
 
@@ -78,44 +78,12 @@ int64_t tq_launch_count(void) { return tq::g_launches; }
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
-int tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride, int device, void *stream,
-                   tq_plan **out)
+// Build a plan from locus runs given as (first column, length) in column order.
+static int build_plan(const std::vector<uint32_t> &run_start, const std::vector<uint32_t> &run_len, int64_t ncols,
+                      int device, void *stream, tq_plan **out)
 {
-    if (!out) return fail(TQ_EINVAL, "tq_plan_create: out is NULL");
-    *out = nullptr;
-    if (ncols < 0 || stride < 1 || (ncols > 0 && !h_locus))
-        return fail(TQ_EINVAL, "tq_plan_create: bad arguments (ncols=%lld stride=%lld)",
-                    (long long)ncols, (long long)stride);
-    if (ncols >= ((int64_t)1 << 32)) return fail(TQ_EINVAL, "tq_plan_create: ncols must be < 2^32");
-
-    // 1. locus runs (maximal runs of equal id, resolve_quartets.py:58-64)
-    std::vector<uint32_t> run_start, run_len;
-    bool monotone = true;
-    {
-        uint32_t prev = 0;
-        for (int64_t c = 0; c < ncols; ++c) {
-            const uint32_t id = h_locus[c * stride];
-            if (c == 0 || id != prev) {
-                if (c > 0 && id < prev) monotone = false;
-                run_start.push_back((uint32_t)c);
-                run_len.push_back(0);
-            }
-            run_len.back()++;
-            prev = id;
-        }
-    }
     const int64_t nloci = (int64_t)run_start.size();
-    if (!monotone) {   // ids may come in any order, but every id must own exactly one run
-        std::unordered_set<uint32_t> seen;
-        seen.reserve((size_t)nloci * 2);
-        for (int64_t r = 0; r < nloci; ++r)
-            if (!seen.insert(h_locus[(int64_t)run_start[r] * stride]).second)
-                return fail(TQ_ELOCUS,
-                            "locus id %u occurs in more than one run of columns; sort tmpmap by locus",
-                            h_locus[(int64_t)run_start[r] * stride]);
-    }
-
-    // 2. stable counting sort of runs by length, longest first
+    // stable counting sort of runs by length, longest first
     uint32_t max_len = 0;
     for (uint32_t l : run_len) max_len = std::max(max_len, l);
     std::vector<int64_t> bucket((size_t)max_len + 2, 0);
@@ -124,14 +92,15 @@ int tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride, int d
     const int64_t ntiles = (nloci + tq::kTileLoci - 1) / tq::kTileLoci;
     const int64_t lpad = ntiles * tq::kTileLoci;
     std::vector<uint32_t> tables;
-    // layout: tile_off[ntiles+1] | tile_k[ntiles] | loc_start[lpad] | loc_len[lpad]
+    // layout: tile_off[ntiles+1] | tile_k[ntiles] | loc_start[lpad] | loc_len[lpad] | loc_run[lpad]
     const size_t o_off = 0, o_k = (size_t)ntiles + 1, o_start = o_k + (size_t)ntiles,
-                 o_len = o_start + (size_t)lpad, total = o_len + (size_t)lpad;
+                 o_len = o_start + (size_t)lpad, o_run = o_len + (size_t)lpad, total = o_run + (size_t)lpad;
     tables.assign(total + 4, 0u);
     for (int64_t r = 0; r < nloci; ++r) {
         const int64_t pos = bucket[max_len - run_len[r]]++;
         tables[o_start + pos] = run_start[r];
         tables[o_len + pos] = run_len[r];
+        tables[o_run + pos] = (uint32_t)r;
     }
     int64_t off = 0, padded = 0;
     for (int64_t t = 0; t < ntiles; ++t) {
@@ -149,7 +118,7 @@ int tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride, int d
     p->device = device;
     p->ncols = ncols; p->nloci = nloci; p->ntiles = ntiles; p->row_u4 = off;
     p->max_len = max_len; p->padded_cols = padded;
-    p->o_off = o_off; p->o_k = o_k; p->o_start = o_start; p->o_len = o_len;
+    p->o_off = o_off; p->o_k = o_k; p->o_start = o_start; p->o_len = o_len; p->o_run = o_run;
     p->dev.ntiles = (int)ntiles;
     p->dev.row_u4 = (uint32_t)off;
     if (device < 0) {               // host-only plan: layout queries, no kernels
@@ -164,8 +133,7 @@ int tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride, int d
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(p->d_tables, tables.data(), (total + 4) * sizeof(uint32_t),
                             cudaMemcpyHostToDevice, (cudaStream_t)stream);
-    // `tables` is pageable: the async copy stages it before returning, so it may go out of scope
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);   // `tables` is pageable
     if (e != cudaSuccess) {
         if (p->d_tables) cudaFree(p->d_tables);
         delete p;
@@ -176,13 +144,68 @@ int tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride, int d
     p->dev.tile_k = base + o_k;
     p->dev.loc_start = base + o_start;
     p->dev.loc_len = base + o_len;
+    p->dev.loc_run = base + o_run;
     p->h_tables.swap(tables);
     *out = p;
     return TQ_OK;
 }
 
+int tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride, int device, void *stream,
+                   tq_plan **out)
+{
+    if (!out) return fail(TQ_EINVAL, "tq_plan_create: out is NULL");
+    *out = nullptr;
+    if (ncols < 0 || stride < 1 || (ncols > 0 && !h_locus))
+        return fail(TQ_EINVAL, "tq_plan_create: bad arguments (ncols=%lld stride=%lld)",
+                    (long long)ncols, (long long)stride);
+    if (ncols >= ((int64_t)1 << 32)) return fail(TQ_EINVAL, "tq_plan_create: ncols must be < 2^32");
+
+    // locus runs (maximal runs of equal id, resolve_quartets.py:58-64)
+    std::vector<uint32_t> run_start, run_len;
+    bool monotone = true;
+    {
+        uint32_t prev = 0;
+        for (int64_t c = 0; c < ncols; ++c) {
+            const uint32_t id = h_locus[c * stride];
+            if (c == 0 || id != prev) {
+                if (c > 0 && id < prev) monotone = false;
+                run_start.push_back((uint32_t)c);
+                run_len.push_back(0);
+            }
+            run_len.back()++;
+            prev = id;
+        }
+    }
+    if (!monotone) {   // ids may come in any order, but every id must own exactly one run
+        std::unordered_set<uint32_t> seen;
+        seen.reserve(run_start.size() * 2);
+        for (size_t r = 0; r < run_start.size(); ++r)
+            if (!seen.insert(h_locus[(int64_t)run_start[r] * stride]).second)
+                return fail(TQ_ELOCUS,
+                            "locus id %u occurs in more than one run of columns; sort tmpmap by locus",
+                            h_locus[(int64_t)run_start[r] * stride]);
+    }
+    return build_plan(run_start, run_len, ncols, device, stream, out);
+}
+
+int tq_plan_create_runs(const uint32_t *h_run_len, int64_t nruns, int device, void *stream, tq_plan **out)
+{
+    if (!out) return fail(TQ_EINVAL, "tq_plan_create_runs: out is NULL");
+    *out = nullptr;
+    if (nruns < 0 || (nruns > 0 && !h_run_len)) return fail(TQ_EINVAL, "tq_plan_create_runs: bad arguments");
+    std::vector<uint32_t> run_start((size_t)nruns), run_len(h_run_len, h_run_len + nruns);
+    int64_t col = 0;
+    for (int64_t r = 0; r < nruns; ++r) {
+        if (run_len[r] == 0) return fail(TQ_EINVAL, "tq_plan_create_runs: run %lld is empty", (long long)r);
+        run_start[r] = (uint32_t)col;
+        col += run_len[r];
+        if (col >= ((int64_t)1 << 32)) return fail(TQ_EINVAL, "tq_plan_create_runs: more than 2^32 columns");
+    }
+    return build_plan(run_start, run_len, col, device, stream, out);
+}
+
 int tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k, uint32_t *loc_start,
-                   uint32_t *loc_len)
+                   uint32_t *loc_len, uint32_t *loc_run)
 {
     if (!plan) return fail(TQ_EINVAL, "tq_plan_tables: plan is NULL");
     const uint32_t *t = plan->h_tables.data();
@@ -191,6 +214,7 @@ int tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k, ui
     if (tile_k) memcpy(tile_k, t + plan->o_k, nt * sizeof(uint32_t));
     if (loc_start) memcpy(loc_start, t + plan->o_start, lp * sizeof(uint32_t));
     if (loc_len) memcpy(loc_len, t + plan->o_len, lp * sizeof(uint32_t));
+    if (loc_run) memcpy(loc_run, t + plan->o_run, lp * sizeof(uint32_t));
     return TQ_OK;
 }
 
@@ -228,6 +252,22 @@ int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t
     if (((uintptr_t)d_planes & 15u) != 0) return fail(TQ_EINVAL, "tq_pack: d_planes must be 16-byte aligned");
     DeviceGuard guard(plan->device);
     TQ_CUDA(tq::launch_pack(plan->dev, d_tmparr, ntips, row_stride, d_planes, (cudaStream_t)stream));
+    return TQ_OK;
+}
+
+int tq_boot_pack(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
+                 const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
+                 uint32_t *d_srccol, uint32_t *d_planes, void *stream)
+{
+    if (!plan) return fail(TQ_EINVAL, "tq_boot_pack: plan is NULL");
+    if (plan->device < 0) return fail(TQ_EINVAL, "tq_boot_pack: host-only plan (device < 0)");
+    if (ntips < 0 || ntips > 65535) return fail(TQ_EINVAL, "tq_boot_pack: ntips=%lld out of range", (long long)ntips);
+    if (ntips == 0 || plan->row_u4 == 0) return TQ_OK;
+    if (!d_seqarr || !d_src_start || !d_srccol || !d_planes) return fail(TQ_EINVAL, "tq_boot_pack: NULL device pointer");
+    if (((uintptr_t)d_planes & 15u) != 0) return fail(TQ_EINVAL, "tq_boot_pack: d_planes must be 16-byte aligned");
+    DeviceGuard guard(plan->device);
+    TQ_CUDA(tq::launch_boot_pack(plan->dev, d_seqarr, ntips, row_stride, d_src_start, seed_shuffle, seed_ambig,
+                                 d_srccol, d_planes, (cudaStream_t)stream));
     return TQ_OK;
 }
 
@@ -330,7 +370,7 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
     if (!same) {
         if (c->plan) { tq_plan_destroy(c->plan); c->plan = nullptr; }
         if ((rc = tq_plan_create(h_locus, ncols, locus_stride, c->device, c->stream, &c->plan)) != TQ_OK) return rc;
-        c->last_h2d += (int64_t)((2 * c->plan->ntiles + 1 + 2 * c->plan->ntiles * tq::kTileLoci) * 4);
+        c->last_h2d += (int64_t)((2 * c->plan->ntiles + 1 + 3 * c->plan->ntiles * tq::kTileLoci) * 4);
         const size_t arr_bytes = (size_t)ntips * (size_t)ncols;
         if ((rc = grow(&c->d_tmparr, &c->cap_tmparr, arr_bytes + 16)) != TQ_OK) return rc;
         if ((rc = grow(&c->d_planes, &c->cap_planes, (size_t)ntips * (size_t)c->plan->row_u4 * 16 + 16)) != TQ_OK) return rc;

@@ -14,12 +14,17 @@ struct PlanDev {
     const uint32_t *tile_k;     // [ntiles]   ranks (max locus length) of the tile
     const uint32_t *loc_start;  // [ntiles*1024] first column of sorted locus l (pad: 0)
     const uint32_t *loc_len;    // [ntiles*1024] columns of sorted locus l      (pad: 0)
+    const uint32_t *loc_run;    // [ntiles*1024] index of the locus run before the length sort
     int      ntiles;
     uint32_t row_u4;            // uint4 per tip row
 };
 
 cudaError_t launch_pack(const PlanDev &plan, const uint8_t *d_tmparr, int64_t ntips,
                         int64_t row_stride, uint32_t *d_planes, cudaStream_t stream);
+
+cudaError_t launch_boot_pack(const PlanDev &plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
+                             const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
+                             uint32_t *d_srccol, uint32_t *d_planes, cudaStream_t stream);
 
 cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips,
                            const uint32_t *d_quartets, int64_t m, bool subsample, uint64_t seed,

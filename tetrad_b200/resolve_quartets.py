@@ -141,6 +141,7 @@ class QuartetResolver:
         self.planes = None
         self.ntips = 0
         self.tmparr_dev = None
+        self.seqarr_dev = None
 
     # -- replicate state -----------------------------------------------------------------
     def _stream(self) -> int:
@@ -179,6 +180,46 @@ class QuartetResolver:
         self.planes = torch.empty((self.ntips, max(4, self.info["row_words"])), dtype=torch.int32,
                                   device=self.device)
         self.pack()
+        return self
+
+    def load_bootstrap(self, seqarr, spans, lidxs, seed_shuffle: int, seed_ambig: int) -> "QuartetResolver":
+        """Build a bootstrap replicate on the device (``tq_plan_create_runs`` + ``tq_boot_pack``).
+
+        ``seqarr`` (numpy u8[n,S0] or a CUDA uint8 tensor already resident from an earlier call):
+        the database's ASCII matrix (``-`` already mapped to ``N``; ambiguity codes unresolved);
+        ``spans`` i64[L,2]; ``lidxs``: the loci drawn with replacement for this replicate
+        (``rng.choice(L, L)`` of the reference, run_inference.py:117); the two seeds are the two
+        31-bit integers the reference draws next (:120, :123)."""
+        torch = self.torch
+        spans = np.asarray(spans, dtype=np.int64)
+        lidxs = np.asarray(lidxs, dtype=np.int64)
+        lens = np.ascontiguousarray(spans[lidxs, 1] - spans[lidxs, 0], dtype=np.uint32)
+        starts = np.ascontiguousarray(spans[lidxs, 0], dtype=np.uint32)
+        self.close()
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tq_plan_create_runs(lens.ctypes.data, len(lens), self.device.index,
+                                                    self._stream(), ctypes.byref(h)))
+        self.plan = h.value
+        info = (ctypes.c_int64 * 8)()
+        _lib.check(self.lib.tq_plan_info(self.plan, info))
+        self.info = dict(ncols=info[0], nloci=info[1], ntiles=info[2], row_words=info[3],
+                         max_len=info[4], padded_cols=info[5])
+        if isinstance(seqarr, torch.Tensor):
+            dev = seqarr if seqarr.device == self.device and seqarr.dtype == torch.uint8 and seqarr.is_contiguous() \
+                else seqarr.to(self.device, dtype=torch.uint8).contiguous()
+        else:
+            dev = torch.from_numpy(np.ascontiguousarray(seqarr, dtype=np.uint8)).to(self.device)
+        self.seqarr_dev = dev
+        self.ntips = int(dev.shape[0])
+        src = torch.from_numpy(starts.view(np.int32)).to(self.device)
+        scratch = torch.empty(max(1, self.info["padded_cols"]), dtype=torch.int32, device=self.device)
+        self.planes = torch.empty((self.ntips, max(4, self.info["row_words"])), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.tq_boot_pack(self.plan, dev.data_ptr(), self.ntips, dev.stride(0), src.data_ptr(),
+                                         int(seed_shuffle) & 0xFFFFFFFF, int(seed_ambig) & 0xFFFFFFFF,
+                                         scratch.data_ptr(), self.planes.data_ptr(), self._stream()))
+        self.tmparr_dev = None
+        self._keep = (src, scratch)          # alive until the kernels have run
         return self
 
     def pack(self):

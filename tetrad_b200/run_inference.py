@@ -178,11 +178,23 @@ def infer_supertree(proj: Project, idx: int, weights: int, min_snps: int = 0, mi
 # ----------------------------------------------------------------------------------------------
 # replicate loop (reference :360-407)
 # ----------------------------------------------------------------------------------------------
-def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int = 0, resolver=None) -> None:
+def draw_bootstrap(spans: np.ndarray, rng: np.random.Generator):
+    """The three draws ``resample_tmp_database`` takes from the project's generator
+    (run_inference.py:117, :120, :123): (lidxs, seed_shuffle, seed_ambig)."""
+    nloci = spans.shape[0]
+    lidxs = rng.choice(nloci, nloci, replace=True)
+    return lidxs, int(rng.integers(2**31)), int(rng.integers(2**31))
+
+
+def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int = 0, resolver=None,
+                  device_bootstrap: bool = True) -> None:
     """Resolve replicate 0 (original data) and ``nboots`` bootstrap replicates, checkpointing
     after each one exactly like the reference (:405-407).  ``ncores`` is accepted for CLI
     compatibility and ignored: the work runs on the GPU(s).  ``resolver`` (tests) overrides the
-    engine: any object with ``load(tmparr, tmpmap)`` and ``resolve(quartets, subsample)``."""
+    engine: any object with ``load(tmparr, tmpmap)`` and ``resolve(quartets, subsample)``.
+    With ``device_bootstrap`` (default) and an engine that has ``load_bootstrap``, replicates >= 1
+    are shuffled, ambiguity-resolved and packed on the GPU from the resident ``seqarr``; otherwise
+    the host builds ``tmparr``/``tmpmap`` (``resample_arrays``) and the engine packs them."""
     import torch
     import torch.distributed as dist
     from . import sharding
@@ -203,13 +215,18 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
     full = combinations.all_quartets(proj.nsamples) if proj.nqrts == proj.nqrts_total else None
     while proj.bootstrap_idx <= nboots:
         # the reference's quartet generator is lazy: its draw happens after the resampling draws
-        if proj.bootstrap_idx:
-            tmparr, tmpmap = resample_arrays(arrays["seqarr"], arrays["spans"], rng)
+        on_device = device_bootstrap and hasattr(resolver, "load_bootstrap")
+        if proj.bootstrap_idx and on_device:
+            lidxs, seed_shuffle, seed_ambig = draw_bootstrap(arrays["spans"], rng)
+            seq = getattr(resolver, "seqarr_dev", None)
+            resolver.load_bootstrap(seq if seq is not None else arrays["seqarr"], arrays["spans"], lidxs,
+                                    seed_shuffle, seed_ambig)
+        elif proj.bootstrap_idx:
+            resolver.load(*resample_arrays(arrays["seqarr"], arrays["spans"], rng))
         else:
-            tmparr, tmpmap = arrays["tmparr"], arrays["tmpmap"]
+            resolver.load(arrays["tmparr"], arrays["tmpmap"])
         quartets = full if full is not None else combinations.random_quartets(proj.nsamples, proj.nqrts, rng)
 
-        resolver.load(tmparr, tmpmap)
         q_dev = torch.from_numpy(quartets.view(np.int32))
         if hasattr(resolver, "device"):
             q_dev = q_dev.to(resolver.device)
