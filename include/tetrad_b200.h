@@ -144,6 +144,7 @@ int tq_ctx_last_traffic(const tq_ctx *ctx, int64_t out[2]);
  * Measurement helpers (bench.py): pipe micro-benchmarks on `device`.
  * kind 0: POPC  (result: popc32 thread-instructions per second)
  * kind 1: LOP3  (and/or)      kind 2: DFMA        kind 3: device copy (bytes/s, read+write)
+ * kind 10..14: POPC rate at 16 warps/SM when mixed with nothing / SHFL / LDS.128 / DFMA / ALU work
  */
 int tq_microbench(int device, int kind, double *result);
 

@@ -417,7 +417,7 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
 
 int tq_microbench(int device, int kind, double *result)
 {
-    if (!result || kind < 0 || kind > 3) return fail(TQ_EINVAL, "tq_microbench: bad arguments");
+    if (!result || kind < 0 || (kind > 3 && (kind < 10 || kind > 14))) return fail(TQ_EINVAL, "tq_microbench: bad arguments");
     DeviceGuard guard(device);
     TQ_CUDA(tq::run_microbench(kind, result));
     return TQ_OK;

@@ -27,8 +27,11 @@ namespace tq {
 int64_t g_launches = 0;
 
 static constexpr unsigned kFull = 0xFFFFFFFFu;
+#ifndef TQ_TMEM
+#define TQ_TMEM 1                             // 1: packed pattern counters live in tensor memory (tcgen05.ld/st)
+#endif
 #ifndef TQ_MIN_CTAS
-#define TQ_MIN_CTAS 4                         // resident CTAs per SM the register budget is sized for
+#define TQ_MIN_CTAS (TQ_TMEM ? 5 : 4)         // resident CTAs per SM the register budget is sized for
 #endif
 static constexpr int kWarps = 4;              // warps (= quartets in flight) per CTA
 static constexpr int kLdm = 18;               // padded column length of the smem matrices (doubles)
@@ -237,6 +240,49 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+#if TQ_TMEM
+// Tensor memory as an accumulator file.  Each CTA (4 warps) allocates 64 TMEM columns; warp w owns
+// TMEM lanes 32w..32w+31 of those columns (a warp may only touch its own lane quadrant), i.e. every
+// thread has 64 private 32-bit cells = its 64 packed counters, which therefore do not occupy
+// registers across tiles.  The 32x32b shape moves N consecutive columns of the thread's own lane.
+static constexpr uint32_t kTmemCols = 64;
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+// 32 patterns (two (a,b) rows x 16 (c,d)) of one word into 16 packed counters
+__device__ __forceinline__ void accumulate32(uint32_t ab0, uint32_t ab1, const uint32_t (&C)[4],
+                                             const uint32_t (&D)[4], uint32_t (&acc)[16])
+{
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t ab = r ? ab1 : ab0;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const uint32_t p0 = __popc(ab & C[h >> 1] & D[2 * (h & 1)]);
+            const uint32_t p1 = __popc(ab & C[h >> 1] & D[2 * (h & 1) + 1]);
+            acc[r * 8 + h] += p0 + (p1 << 16);
+        }
+    }
+}
+#endif
+
 __device__ __forceinline__ void accumulate128(uint32_t A0, uint32_t A1, const uint32_t (&B)[4],
                                               const uint32_t (&C)[4], const uint32_t (&D)[4],
                                               uint32_t (&acc)[64])
@@ -256,6 +302,51 @@ __device__ __forceinline__ void accumulate128(uint32_t A0, uint32_t A1, const ui
 }
 
 // 256 pattern counts of one tile word pair (own word + partner lane's word), split by half-warp.
+#if TQ_TMEM
+__device__ __forceinline__ void count_tile(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                           const uint32_t (&MC)[4], const uint32_t (&MD)[4],
+                                           bool upper, uint32_t tacc)
+{
+    // planes the partner needs from me: the a-planes of ITS half, and all of B, C, D
+    const uint32_t sendA0 = upper ? MA[0] : MA[2], sendA1 = upper ? MA[1] : MA[3];
+    const uint32_t pA0 = __shfl_xor_sync(kFull, sendA0, 16), pA1 = __shfl_xor_sync(kFull, sendA1, 16);
+    uint32_t pB[4], pC[4], pD[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pB[i] = __shfl_xor_sync(kFull, MB[i], 16);
+        pC[i] = __shfl_xor_sync(kFull, MC[i], 16);
+        pD[i] = __shfl_xor_sync(kFull, MD[i], 16);
+    }
+    const uint32_t A0 = upper ? MA[2] : MA[0], A1 = upper ? MA[3] : MA[1];
+    tmem_wait_st();                                  // the previous tile's stores have landed
+    // counters 16g .. 16g+15 hold rows (ai, b) = (g / 2, 2 (g % 2) + {0, 1}).  A runtime loop: the
+    // counters are addressed in tensor memory, so nothing forces the 256 patterns to be unrolled,
+    // and the whole body (64 AND + 64 POPC + 64 add) stays resident in the instruction cache.
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        uint32_t acc[16];
+        tmem_ld16(tacc + 16 * g, acc);
+        const bool hi = (g & 1) != 0;
+        const uint32_t a_own = (g >> 1) ? A1 : A0, a_par = (g >> 1) ? pA1 : pA0;
+        const uint32_t o0 = a_own & (hi ? MB[2] : MB[0]), o1 = a_own & (hi ? MB[3] : MB[1]);
+        const uint32_t q0 = a_par & (hi ? pB[2] : pB[0]), q1 = a_par & (hi ? pB[3] : pB[1]);
+        tmem_wait_ld();
+        accumulate32(o0, o1, MC, MD, acc);
+        accumulate32(q0, q1, pC, pD, acc);
+        tmem_st16(tacc + 16 * g, acc);
+    }
+}
+
+__device__ __forceinline__ void zero_acc(uint32_t tacc)
+{
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+    tmem_wait_st();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) tmem_st16(tacc + 16 * g, z);
+}
+#else
 __device__ __forceinline__ void count_tile(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
                                            const uint32_t (&MC)[4], const uint32_t (&MD)[4],
                                            bool upper, uint32_t (&acc)[64])
@@ -273,6 +364,7 @@ __device__ __forceinline__ void count_tile(const uint32_t (&MA)[4], const uint32
     accumulate128(upper ? MA[2] : MA[0], upper ? MA[3] : MA[1], MB, MC, MD, acc);
     accumulate128(pA0, pA1, pB, pC, pD, acc);
 }
+#endif
 
 // Butterfly-add the packed counters over the 16 lanes of each half-warp, add into T, clear.
 __device__ __forceinline__ void flush_acc(uint32_t (&acc)[64], uint32_t *T, int lane)
@@ -309,18 +401,58 @@ __device__ __forceinline__ void issue_chunk(uint32_t ring_s, const uint4 *__rest
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1536), "l"(planes + (t3 + lane_nu)) : "memory");
 }
 
+#if TQ_TMEM
+// Read the 64 packed counters back from tensor memory, butterfly-add them over the 16 lanes of
+// each half-warp, add into T, and clear them.  Runtime loop over the four groups (code size).
+__device__ __noinline__ void flush_tmem(uint32_t tacc, uint32_t *T, int lane)
+{
+    const int abase = (lane >> 4) * 2;           // first a-value of this half-warp
+    tmem_wait_st();
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        uint32_t part[16];
+        tmem_ld16(tacc + 16 * g, part);
+        tmem_wait_ld();
+        uint32_t *row = T + ((abase + (g >> 1)) * 4 + 2 * (g & 1)) * 16;      // pattern (a, b = 2(g%2), cd = 0)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            uint32_t v = part[k];
+            v += __shfl_xor_sync(kFull, v, 8);
+            v += __shfl_xor_sync(kFull, v, 4);
+            v += __shfl_xor_sync(kFull, v, 2);
+            v += __shfl_xor_sync(kFull, v, 1);
+            if ((lane & 15) == k) {                                            // k = 8 (b & 1) + h
+                uint2 *t = reinterpret_cast<uint2 *>(row + (k >> 3) * 16 + 2 * (k & 7));
+                uint2 cur = *t;
+                cur.x += v & 0xFFFFu;
+                cur.y += v >> 16;
+                *t = cur;
+            }
+            part[k] = 0u;
+        }
+        tmem_st16(tacc + 16 * g, part);
+    }
+}
+#endif
+
 template <bool kSubsample>
 __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *__restrict__ planes,
-                                              uint4 tips, WarpScratch &ws, int lane, uint32_t debug
+                                              uint4 tips, WarpScratch &ws, int lane, uint32_t debug, uint32_t tacc
 #ifdef TQ_PHASE_TIMERS
                                               , long long (&ph)[8]
 #endif
                                               )
 {
     TQ_T0();
+#if TQ_TMEM
+    const uint32_t acc = tacc;                     // handle of this thread's 64 counters in tensor memory
+#define TQ_FLUSH() flush_tmem(acc, ws.T, lane)
+#else
     uint32_t acc[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) acc[i] = 0u;
+#define TQ_FLUSH() flush_acc(acc, ws.T, lane)
+#endif
     const bool upper = lane >= 16;
     uint32_t pending = 0;
     const uint32_t nchunks = plan.row_u4 / kTileWords;
@@ -370,19 +502,20 @@ __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *
                 const uint32_t A[4] = {a.x, a.y, a.z, a.w}, B[4] = {b.x, b.y, b.z, b.w};
                 const uint32_t C[4] = {c.x, c.y, c.z, c.w}, D[4] = {d.x, d.y, d.z, d.w};
                 count_tile(A, B, C, D, upper, acc);
-                if (++pending == kFlushEvery) { flush_acc(acc, ws.T, lane); pending = 0; }
+                if (++pending == kFlushEvery) { TQ_FLUSH(); pending = 0; }
             }
         }
         TQ_ACC(0);
         if (kSubsample && !(debug & 2u)) {
             count_tile(MA, MB, MC, MD, upper, acc);
-            if (++pending == kFlushEvery) { flush_acc(acc, ws.T, lane); pending = 0; }
+            if (++pending == kFlushEvery) { TQ_FLUSH(); pending = 0; }
         }
         TQ_ACC(1);
     }
     cp_async_wait<0>();
-    flush_acc(acc, ws.T, lane);
+    TQ_FLUSH();
     TQ_ACC(2);
+#undef TQ_FLUSH
 }
 
 // ------------------------------------------------------------------------------------------
@@ -499,7 +632,7 @@ __device__ __noinline__ void svd_scores(WarpScratch &ws, int lane, double *score
 #pragma unroll
         for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
         bool big = false;
-#pragma unroll
+#pragma unroll 1
         for (int g = 8; g >= 1; g >>= 1) {
             for (int r = 0; r < g; ++r) {
                 jacobi_rotate(P, Q, nP, nQ, tiny, big, (debug & 64u) != 0);
@@ -612,6 +745,22 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tq_start = clock64();
 #endif
+#if TQ_TMEM
+    __shared__ uint32_t tmem_base_slot;
+    if (warp == 0) {                                  // one warp allocates (and later frees) the CTA's columns
+        const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&tmem_base_slot);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(slot), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quadrant
+    zero_acc(tacc);
+#else
+    const uint32_t tacc = 0u;
+#endif
 
     // Every quartet costs the same, so co-resident warps would run their count and SVD phases in
     // lock-step and leave the POPC pipe idle during the SVD phases.  Delay the k-th resident CTA of
@@ -637,10 +786,10 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
         for (int i = 0; i < 8; ++i) ws.T[lane + 32 * i] = 0u;
         __syncwarp();
 #ifdef TQ_PHASE_TIMERS
-        count_quartet<kSubsample>(plan, planes, t, ws, lane, debug, ph);
+        count_quartet<kSubsample>(plan, planes, t, ws, lane, debug, tacc, ph);
         long long tq_t0 = clock64();
 #else
-        count_quartet<kSubsample>(plan, planes, t, ws, lane, debug);
+        count_quartet<kSubsample>(plan, planes, t, ws, lane, debug, tacc);
 #endif
         __syncwarp();
         if (!kSubsample && lane < 4) ws.T[85u * lane] = 0u;   // invariant patterns aaaa, :218
@@ -672,6 +821,13 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
         }
         __syncwarp();
     }
+#if TQ_TMEM
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+#endif
 #ifdef TQ_PHASE_TIMERS
     if (lane == 0) {
         for (int i = 0; i < 4; ++i) atomicAdd(&g_phase_clk[i], (unsigned long long)ph[i]);
@@ -768,6 +924,43 @@ __global__ void __launch_bounds__(256) pipe_kernel(uint32_t *out, int iters, uin
     }
 }
 
+// POPC mixed with other MIO-queue instructions: kMix 0 = POPC only, 1 = + 4 SHFL per 8 POPC,
+// 2 = + 2 LDS.128 per 8 POPC, 3 = + 8 independent DFMA per 8 POPC, 4 = + 16 LOP3/IADD per 8 POPC
+template <int kMix>
+__global__ void __launch_bounds__(128) mix_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    __shared__ uint4 sm[128];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    sm[threadIdx.x] = make_uint4(tid, seed, tid ^ seed, 7u);
+    __syncthreads();
+    uint32_t v[8], acc[8], extra = seed;
+    double d[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { v[u] = tid * 2654435761u + seed + u; acc[u] = u; d[u] = 1.0 + u; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += __popc(v[u] ^ acc[u]);
+        if (kMix == 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] ^= __shfl_xor_sync(0xFFFFFFFFu, v[u + 4], 16);
+        } else if (kMix == 2) {
+            const uint4 a = sm[(threadIdx.x + it) & 127], b = sm[(threadIdx.x + 2 * it + 1) & 127];
+            extra += a.x ^ a.w ^ b.y ^ b.z;
+        } else if (kMix == 3) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d[u] = fma(d[u], 1.0000001, 1e-9);
+        } else if (kMix == 4) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { v[u] = (v[u] & 0x7FFFFFFFu) + (v[u] >> 3); extra ^= v[u] | acc[u]; }
+        }
+    }
+    uint32_t s = extra;
+    double ds = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s += acc[u] + v[u]; ds += d[u]; }
+    if (s == 0x12345u || ds == 1.5) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
                                                    size_t n)
 {
@@ -786,7 +979,29 @@ cudaError_t run_microbench(int kind, double *result)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     float best_ms = 1e30f;
     double work = 0.0;
-    if (kind == 3) {
+    if (kind >= 10) {   // POPC + other instruction mixes at the resolve kernel's occupancy (16 warps/SM)
+        uint32_t *out = nullptr;
+        if ((err = cudaMalloc(&out, 64)) != cudaSuccess) return err;
+        const int iters = 4096, blocks = sms * 4, threads = 128;
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(e0);
+            switch (kind) {
+            case 10: mix_kernel<0><<<blocks, threads>>>(out, iters, rep); break;
+            case 11: mix_kernel<1><<<blocks, threads>>>(out, iters, rep); break;
+            case 12: mix_kernel<2><<<blocks, threads>>>(out, iters, rep); break;
+            case 13: mix_kernel<3><<<blocks, threads>>>(out, iters, rep); break;
+            default: mix_kernel<4><<<blocks, threads>>>(out, iters, rep); break;
+            }
+            ++g_launches;
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best_ms) best_ms = ms;
+        }
+        cudaFree(out);
+        work = (double)blocks * threads * (double)iters * 8.0;
+    } else if (kind == 3) {
         const size_t bytes = (size_t)1 << 30;
         uint4 *a = nullptr, *b = nullptr;
         if ((err = cudaMalloc(&a, bytes)) != cudaSuccess) return err;
