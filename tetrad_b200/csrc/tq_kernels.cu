@@ -266,20 +266,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
-// 32 patterns (two (a,b) rows x 16 (c,d)) of one word into 16 packed counters
-__device__ __forceinline__ void accumulate32(uint32_t ab0, uint32_t ab1, const uint32_t (&C)[4],
-                                             const uint32_t (&D)[4], uint32_t (&acc)[16])
+// One (a,b) row = 16 patterns.  The ANDs and the POPCs are volatile asm so that ptxas keeps them in
+// the order written: a software pipeline in which every POPC has ~16 independent POPCs and the next
+// row's ANDs between its issue and the add that consumes it (left alone, ptxas puts the consumer 1-3
+// instructions behind the POPC and the warp sits on the XU latency).
+__device__ __forceinline__ void row_and(uint32_t ab, const uint32_t (&C)[4], const uint32_t (&D)[4], uint32_t (&v)[16])
 {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const uint32_t ab = r ? ab1 : ab0;
+    for (int cd = 0; cd < 16; ++cd)
+        asm volatile("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(v[cd]) : "r"(ab), "r"(C[cd >> 2]), "r"(D[cd & 3]));
+}
+__device__ __forceinline__ void row_popc(uint32_t (&v)[16])
+{
 #pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            const uint32_t p0 = __popc(ab & C[h >> 1] & D[2 * (h & 1)]);
-            const uint32_t p1 = __popc(ab & C[h >> 1] & D[2 * (h & 1) + 1]);
-            acc[r * 8 + h] += p0 + (p1 << 16);
-        }
-    }
+    for (int cd = 0; cd < 16; ++cd) asm volatile("popc.b32 %0, %0;" : "+r"(v[cd]));
+}
+__device__ __forceinline__ void row_add(const uint32_t (&v)[16], uint32_t *acc8)
+{
+#pragma unroll
+    for (int h = 0; h < 8; ++h) acc8[h] += v[2 * h] + (v[2 * h + 1] << 16);
 }
 #endif
 
@@ -330,9 +335,20 @@ __device__ __forceinline__ void count_tile(const uint32_t (&MA)[4], const uint32
         const uint32_t a_own = (g >> 1) ? A1 : A0, a_par = (g >> 1) ? pA1 : pA0;
         const uint32_t o0 = a_own & (hi ? MB[2] : MB[0]), o1 = a_own & (hi ? MB[3] : MB[1]);
         const uint32_t q0 = a_par & (hi ? pB[2] : pB[0]), q1 = a_par & (hi ? pB[3] : pB[1]);
+        uint32_t va[16], vb[16];
+        row_and(o0, MC, MD, va);
+        row_popc(va);
+        row_and(o1, MC, MD, vb);
         tmem_wait_ld();
-        accumulate32(o0, o1, MC, MD, acc);
-        accumulate32(q0, q1, pC, pD, acc);
+        row_add(va, acc);
+        row_popc(vb);
+        row_and(q0, pC, pD, va);
+        row_add(vb, acc + 8);
+        row_popc(va);
+        row_and(q1, pC, pD, vb);
+        row_add(va, acc);
+        row_popc(vb);
+        row_add(vb, acc + 8);
         tmem_st16(tacc + 16 * g, acc);
     }
 }
