@@ -39,6 +39,7 @@ sys.path.insert(0, str(ROOT))
 
 from tetrad_b200 import synth  # noqa: E402
 
+print_result = print
 METRIC = "quartets_resolved_per_sec"
 UNIT = "quartets/s"
 
@@ -160,7 +161,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_result(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -314,12 +315,20 @@ def run_ours(args):
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line), flush=True)
+    print_result(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # Only the JSON line may reach stdout (NCCL and torchrun print banners there): route fd 1 to
+    # stderr for the whole run and write the result to the saved descriptor at the end.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    global print_result
+    print_result = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
