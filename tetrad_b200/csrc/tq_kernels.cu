@@ -640,7 +640,92 @@ __device__ __noinline__ void svd_scores(WarpScratch &ws, int lane, double *score
 #pragma unroll
         for (int r = 0; r < 16; ++r) { P[r] = 0.0; Q[r] = 0.0; }
     }
-    __syncwarp();                                    // M is free from here on: reuse it as xbuf
+    __syncwarp();                                    // M is free from here on: reuse it below
+
+    // Preconditioner (Drmac-Veselic): A P = Q R by modified Gram-Schmidt with column pivoting, then
+    // Jacobi on the ROWS of R instead of the columns of A -- same singular values, ~40 % fewer sweeps
+    // (numpy model: 9.4 -> 5.5 per quartet).  Lane (m, s) still owns columns s and s+8 of A; step k
+    // picks the remaining column of largest norm, broadcasts it inside the 8-lane group, and every lane
+    // writes r_kj = q_k . a_j for its two columns to W[m][k][j] (j = ORIGINAL column index: a column
+    // permutation of R does not change its singular values) and removes that component.
+    if (!(debug & 128u)) {
+        double *W = &sv.M[0][0][0];                  // [3][16 rows k][16 cols j], 6 KB
+        bool doneP = lane >= 24, doneQ = lane >= 24;
+        double mP = 0.0, mQ = 0.0;                   // squared norms of the remaining parts of P, Q
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            if ((k & 3) == 0) {                      // exact every 4th step, downdated in between
+                mP = 0.0; mQ = 0.0;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { mP = fma(P[r], P[r], mP); mQ = fma(Q[r], Q[r], mQ); }
+            }
+            const double nP = doneP ? -1.0 : mP, nQ = doneQ ? -1.0 : mQ;
+            double best = (nP >= nQ) ? nP : nQ;
+            int idx = (nP >= nQ) ? s : s + 8;
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(kFull, best, off);
+                const int oi = __shfl_xor_sync(kFull, idx, off);
+                if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+            }
+            const bool any = best >= 0.0;            // a column of this matrix is still unprocessed
+            // the pivot column goes through shared memory (one writer per 8-lane group)
+            double2 *pv = reinterpret_cast<double2 *>(&sv.srt[lane < 24 ? m : 0][0]);
+            if (lane < 24 && idx == s) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) pv[r] = make_double2(P[2 * r], P[2 * r + 1]);
+            } else if (lane < 24 && idx == s + 8) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) pv[r] = make_double2(Q[2 * r], Q[2 * r + 1]);
+            }
+            __syncwarp();
+            double dP = 0.0, dQ = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double2 x = pv[r];
+                dP = fma(x.x, P[2 * r], dP); dP = fma(x.y, P[2 * r + 1], dP);
+                dQ = fma(x.x, Q[2 * r], dQ); dQ = fma(x.y, Q[2 * r + 1], dQ);
+            }
+            // 1/sqrt(|a_p|^2) from the pivot's own dot product (exact norm, not the downdated one)
+            const double pp = __shfl_sync(kFull, (idx == s) ? dP : dQ, (lane & ~7) | (idx & 7));
+            const bool live = any && pp > tiny;      // else the pivot is a null direction: retire it with a zero row
+            const double safe = live ? pp : 1.0;
+            double rinv;
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(safe));
+            rinv = rinv * fma(-0.5 * safe, rinv * rinv, 1.5);
+            rinv = rinv * fma(-0.5 * safe, rinv * rinv, 1.5);
+            const double inv = rinv * rinv;
+            const bool useP = live && !doneP, useQ = live && !doneQ;
+            const double rP = useP ? dP * rinv : 0.0, rQ = useQ ? dQ * rinv : 0.0;
+            if (lane < 24) {
+                W[(m * 16 + k) * 16 + s] = rP;
+                W[(m * 16 + k) * 16 + s + 8] = rQ;
+            }
+            mP = fmax(fma(-rP, rP, mP), 0.0);
+            mQ = fmax(fma(-rQ, rQ, mQ), 0.0);
+            const double cP = useP ? -dP * inv : 0.0, cQ = useQ ? -dQ * inv : 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double2 x = pv[r];
+                P[2 * r] = fma(cP, x.x, P[2 * r]); P[2 * r + 1] = fma(cP, x.y, P[2 * r + 1]);
+                Q[2 * r] = fma(cQ, x.x, Q[2 * r]); Q[2 * r + 1] = fma(cQ, x.y, Q[2 * r + 1]);
+            }
+            __syncwarp();
+            if (any && idx == s) doneP = true;
+            if (any && idx == s + 8) doneQ = true;
+        }
+        __syncwarp();
+        if (lane < 24) {                             // rows s and s+8 of R become this lane's columns
+            const double2 *cp = reinterpret_cast<const double2 *>(W + (m * 16 + s) * 16);
+            const double2 *cq = reinterpret_cast<const double2 *>(W + (m * 16 + s + 8) * 16);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double2 x = cp[r], y = cq[r];
+                P[2 * r] = x.x; P[2 * r + 1] = x.y; Q[2 * r] = y.x; Q[2 * r + 1] = y.y;
+            }
+        }
+        __syncwarp();
+    }
     double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][9 double2] (144 B stride)
 
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
