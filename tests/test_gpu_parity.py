@@ -198,3 +198,43 @@ def test_tetrad_facade_and_cli_end_to_end(tb, oracle, tmp_path):
     # engine entry point with the reference's signature
     rq, rstat, rscor = tb.infer_resolved_quartets(cproj.database_file, 8, [(0, 1, 2, 3), (1, 3, 5, 7)], False)
     assert rstat.shape == (2, 2) and rscor.shape == (2, 3) and rq.shape == (2, 4)
+
+
+def _matrix_from_counts(T):
+    """4 x S code matrix (one column per counted SNP, every column its own locus) realising the
+    count tensor T[a,b,c,d] exactly."""
+    pats = np.repeat(np.arange(256), T.reshape(-1))
+    arr = np.stack([(pats >> 6) & 3, (pats >> 4) & 3, (pats >> 2) & 3, pats & 3]).astype(np.uint8)
+    tmpmap = np.stack([np.arange(arr.shape[1]), np.arange(arr.shape[1])], 1).astype(np.uint32)
+    return arr, tmpmap
+
+
+def test_crafted_count_tensors_exercise_the_svd(tb, oracle):
+    """Singular-value epilogue on count tensors chosen for their spectra: rank 1..5, repeated
+    singular values, seven orders of magnitude of dynamic range, dense random, near-duplicates."""
+    rng = np.random.default_rng(12)
+    tensors = []
+    for rank in (1, 2, 3, 5):                                     # few non-zero patterns
+        T = np.zeros(256, np.int64)
+        T[rng.choice(256, rank, replace=False)] = rng.integers(1, 400, rank)
+        tensors.append(T)
+    T = np.zeros((4, 4, 4, 4), np.int64); T[0, 1, 0, 1] = T[1, 0, 1, 0] = T[2, 3, 2, 3] = T[3, 2, 3, 2] = 100
+    tensors.append(T.reshape(-1))                                 # four equal singular values
+    T = rng.integers(0, 3, 256); T[17] = 60000; T[200] = 9000
+    tensors.append(T)                                             # large dynamic range
+    tensors.append(rng.integers(0, 60, 256))                      # dense, full rank
+    T = np.zeros((16, 16), np.int64); T[:, :] = rng.integers(1, 30, 16)[None, :]; T[5, 5] += 1
+    tensors.append(T.reshape(-1))                                 # rank 1 plus one perturbed entry
+    tensors.append(np.outer(rng.integers(1, 9, 16), rng.integers(1, 9, 16)).reshape(-1))   # exact rank 1, dense
+    quartet = np.array([[0, 1, 2, 3]], dtype=np.uint32)
+    for T in tensors:
+        T = np.asarray(T, np.int64).copy()
+        T[[0, 85, 170, 255]] = 0                                  # invariant patterns are never counted
+        arr, tmpmap = _matrix_from_counts(T)
+        for sub in (True, False):
+            _, rstat, rscor, extra = tb.new_infer_resolved_quartets(arr, tmpmap, quartet, sub, return_counts=True)
+            _, ostat, oscor, det = oracle.new_infer_resolved_quartets(arr, tmpmap, quartet, sub, return_details=True)
+            assert (extra["counts"].reshape(-1) == T).all()
+            assert extra["minrank"][0] == det["minrank"][0], (T.nonzero()[0][:8], extra["minrank"], det["ranks"])
+            assert_scores_close(rscor, oscor, ostat[:, 1])
+            assert_best_matches(rstat[:, 0], oscor, ostat)
