@@ -85,6 +85,17 @@ int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t
             uint32_t *d_planes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Quartet unranking on the device.  Replaces _index_to_combination / iter_chunks_full
+ * (tetrad/src/combinations.py:82-106): lexicographic rank in itertools.combinations(range(ntips), 4)
+ * -> four ascending tip ids, written to d_quartets u32[m][4].  d_ranks i64[m] (device) gives the ranks
+ * (e.g. the reference's rng.choice(C(n,4), size, replace=False) sample); with d_ranks = NULL the
+ * ranks are the contiguous range [start, start + m) -- the exhaustive enumeration, no upload at all.
+ * Ranks must be < C(ntips, 4) (checked for the range form only).
+ */
+int tq_unrank(int device, const int64_t *d_ranks, int64_t start, int64_t m, int64_t ntips,
+              uint32_t *d_quartets, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * K2/K5: bootstrap replicate packed on the device.  Replaces resample_tmp_database + jit_resample +
  * jit_resolve_ambigs (run_inference.py:99-143, tetrad/jit/resample.py:20-64,
  * tetrad/jit/resolve_ambigs.py:12-36) for replicates >= 1: `plan` comes from

@@ -238,3 +238,25 @@ def test_crafted_count_tensors_exercise_the_svd(tb, oracle):
             assert extra["minrank"][0] == det["minrank"][0], (T.nonzero()[0][:8], extra["minrank"], det["ranks"])
             assert_scores_close(rscor, oscor, ostat[:, 1])
             assert_best_matches(rstat[:, 0], oscor, ostat)
+
+
+def test_device_unranking_matches_itertools_and_reference_vectors(tb):
+    from itertools import combinations
+    from math import comb
+    from tetrad_b200 import combinations as cb
+    from tetrad_b200._lib import TetradB200Error
+    for n in (4, 5, 12, 37):
+        want = np.array(list(combinations(range(n), 4)), dtype=np.int32)
+        assert (cb.device_quartets(n).cpu().numpy() == want).all()
+    g = load_golden("unrank")
+    assert (cb.device_quartets(12, ranks=g["idx12"]).cpu().numpy().view(np.uint32) == g["comb12"]).all()
+    assert (cb.device_quartets(200, ranks=g["idx200"]).cpu().numpy().view(np.uint32) == g["comb200"]).all()
+    rng = np.random.default_rng(3)
+    ranks = rng.choice(comb(500, 4), size=20000, replace=False)          # C5-sized tip count
+    assert (cb.device_quartets(500, ranks=ranks).cpu().numpy().view(np.uint32) == cb.unrank_quartets(ranks, 500)).all()
+    part = cb.device_quartets(50, start=1000, count=77).cpu().numpy()
+    assert (part == np.array(list(combinations(range(50), 4)), dtype=np.int32)[1000:1077]).all()
+    with pytest.raises(TetradB200Error):
+        cb.device_quartets(10, start=200, count=100)
+    with pytest.raises(ValueError):
+        cb.device_quartets(10, ranks=np.array([comb(10, 4)]))

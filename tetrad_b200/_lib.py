@@ -85,6 +85,8 @@ def _declare(lib):
     lib.tq_plan_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.tq_plan_create_runs.restype = i32
     lib.tq_plan_create_runs.argtypes = [vp, i64, i32, vp, c.POINTER(vp)]
+    lib.tq_unrank.restype = i32
+    lib.tq_unrank.argtypes = [i32, vp, i64, i64, i64, vp, vp]
     lib.tq_boot_pack.restype = i32
     lib.tq_boot_pack.argtypes = [vp, vp, i64, i64, vp, c.c_uint32, c.c_uint32, vp, vp, vp]
     lib.tq_pack.restype = i32
@@ -104,7 +106,7 @@ def _declare(lib):
 
 
 EXPORTS = [
-    "tq_version", "tq_last_error", "tq_launch_count", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack",
+    "tq_version", "tq_last_error", "tq_launch_count", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
     "tq_plan_destroy",
     "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
     "tq_ctx_last_traffic", "tq_microbench",

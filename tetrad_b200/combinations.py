@@ -65,3 +65,26 @@ def iter_chunks_random(nsamples: int, size: int, max_size: int, rng):
     quartets = random_quartets(nsamples, size, rng)
     for lo in range(0, len(quartets), max_size):
         yield quartets[lo: lo + max_size]
+
+
+def device_quartets(nsamples: int, device: int = 0, ranks=None, start: int = 0, count: int | None = None):
+    """Quartets unranked on the GPU (``tq_unrank``): an int32 CUDA tensor [m,4].  ``ranks`` (numpy
+    or CUDA int64) selects a sample; otherwise the contiguous rank range ``[start, start+count)``
+    (default: all C(n,4) quartets) is produced without any host->device copy."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if ranks is not None:
+        r = ranks if isinstance(ranks, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ranks, dtype=np.int64))
+        r = r.to(dev, dtype=torch.int64).contiguous()
+        if r.numel() and (int(r.min()) < 0 or int(r.max()) >= comb(nsamples, 4)):
+            raise ValueError("quartet rank out of range")
+        out = torch.empty((r.numel(), 4), dtype=torch.int32, device=dev)
+        _lib.check(lib.tq_unrank(device, r.data_ptr(), 0, r.numel(), nsamples, out.data_ptr(), stream))
+        return out
+    m = comb(nsamples, 4) - start if count is None else count
+    out = torch.empty((m, 4), dtype=torch.int32, device=dev)
+    _lib.check(lib.tq_unrank(device, None, start, m, nsamples, out.data_ptr(), stream))
+    return out

@@ -255,6 +255,20 @@ int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t
     return TQ_OK;
 }
 
+int tq_unrank(int device, const int64_t *d_ranks, int64_t start, int64_t m, int64_t ntips, uint32_t *d_quartets,
+              void *stream)
+{
+    if (m < 0 || ntips < 4 || ntips > 65535) return fail(TQ_EINVAL, "tq_unrank: bad sizes (m=%lld ntips=%lld)", (long long)m, (long long)ntips);
+    if (m == 0) return TQ_OK;
+    if (!d_quartets || ((uintptr_t)d_quartets & 15u)) return fail(TQ_EINVAL, "tq_unrank: d_quartets must be a 16-byte aligned device pointer");
+    const uint64_t n = (uint64_t)ntips, total = n * (n - 1) / 2 * (n - 2) / 3 * (n - 3) / 4;
+    if (!d_ranks && (start < 0 || (uint64_t)start + (uint64_t)m > total))
+        return fail(TQ_EINVAL, "tq_unrank: range [%lld, %lld) exceeds C(%lld,4)", (long long)start, (long long)(start + m), (long long)ntips);
+    DeviceGuard guard(device);
+    TQ_CUDA(tq::launch_unrank(d_ranks, start, m, (uint32_t)ntips, d_quartets, (cudaStream_t)stream));
+    return TQ_OK;
+}
+
 int tq_boot_pack(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
                  const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
                  uint32_t *d_srccol, uint32_t *d_planes, void *stream)

@@ -84,6 +84,59 @@ cudaError_t launch_pack(const PlanDev &plan, const uint8_t *d_tmparr, int64_t nt
 }
 
 // ------------------------------------------------------------------------------------------
+// Quartet unranking (reference tetrad/src/combinations.py:94-106, _index_to_combination):
+// lexicographic rank in itertools.combinations(range(n), 4) -> (a, b, c, d).  The number of
+// quartets whose first id is < a is C(n,4) - C(n-a,4), and so on down the levels; each level is
+// a binary search on a closed-form binomial (C(n,4) < 2^32 is asserted by the reference).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t choose2(uint64_t m) { return m < 2 ? 0 : m * (m - 1) / 2; }
+__device__ __forceinline__ uint64_t choose3(uint64_t m) { return m < 3 ? 0 : m * (m - 1) / 2 * (m - 2) / 3; }
+__device__ __forceinline__ uint64_t choose4(uint64_t m) { return m < 4 ? 0 : m * (m - 1) / 2 * (m - 2) / 3 * (m - 3) / 4; }
+
+// smallest m in [lo, hi] with f(m) >= x  (f non-decreasing)
+template <typename F>
+__device__ __forceinline__ uint32_t lower_bound_fn(uint32_t lo, uint32_t hi, uint64_t x, F f)
+{
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (f(mid) >= x) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) unrank_kernel(const int64_t *__restrict__ ranks, int64_t start, int64_t m,
+                                                     uint32_t n, uint4 *__restrict__ quartets)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint64_t r = (uint64_t)(ranks ? ranks[i] : start + i);
+    const uint64_t total = choose4(n);
+    // first id a: largest a with total - C(n-a,4) <= r  <=>  smallest m1 = n-a with C(m1,4) >= total - r ... (m1 maximal a)
+    const uint32_t m1 = lower_bound_fn(4u, n, total - r, [](uint32_t mm) { return choose4(mm); });
+    const uint32_t a = n - m1;
+    r -= total - choose4(m1);
+    const uint64_t x = choose3(m1 - 1) - r;                         // >= 1
+    const uint32_t m2 = lower_bound_fn(3u, m1 - 1, x, [](uint32_t mm) { return choose3(mm); });
+    const uint32_t b = n - m2;
+    r -= choose3(m1 - 1) - choose3(m2);
+    const uint64_t y = choose2(m2 - 1) - r;
+    const uint32_t m3 = lower_bound_fn(2u, m2 - 1, y, [](uint32_t mm) { return choose2(mm); });
+    const uint32_t c = n - m3;
+    r -= choose2(m2 - 1) - choose2(m3);
+    quartets[i] = make_uint4(a, b, c, c + 1 + (uint32_t)r);
+}
+
+cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint32_t ntips, uint32_t *d_quartets,
+                          cudaStream_t stream)
+{
+    if (m == 0) return cudaSuccess;
+    unrank_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(d_ranks, start, m, ntips,
+                                                                   reinterpret_cast<uint4 *>(d_quartets));
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // K2/K5: bootstrap replicate built on the device (reference resample_tmp_database +
 // jit_resample + jit_resolve_ambigs, run_inference.py:99-143, resample.py:20-64,
 // resolve_ambigs.py:12-36).  The host draws which locus fills instance i (the reference's

@@ -32,6 +32,9 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
                            uint32_t *d_minrank, uint32_t *d_status, int num_sms,
                            cudaStream_t stream);
 
+cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint32_t ntips, uint32_t *d_quartets,
+                          cudaStream_t stream);
+
 cudaError_t run_microbench(int kind, double *result);
 
 extern int64_t g_launches;

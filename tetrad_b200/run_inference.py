@@ -212,7 +212,14 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
         logger.info("continuing quartet tree inference")
         rng = proj.bootstrap_rng.to_rng()
 
-    full = combinations.all_quartets(proj.nsamples) if proj.nqrts == proj.nqrts_total else None
+    exhaustive = proj.nqrts == proj.nqrts_total
+    gpu_index = getattr(getattr(resolver, "device", None), "index", None)      # None for CPU stand-ins (tests)
+    full = full_dev = None
+    if exhaustive and gpu_index is not None:
+        full_dev = combinations.device_quartets(proj.nsamples, gpu_index)       # unranked on the GPU, no upload
+        full = full_dev.cpu().numpy().view(np.uint32)
+    elif exhaustive:
+        full = combinations.all_quartets(proj.nsamples)
     while proj.bootstrap_idx <= nboots:
         # the reference's quartet generator is lazy: its draw happens after the resampling draws
         on_device = device_bootstrap and hasattr(resolver, "load_bootstrap")
@@ -225,11 +232,19 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
             resolver.load(*resample_arrays(arrays["seqarr"], arrays["spans"], rng))
         else:
             resolver.load(arrays["tmparr"], arrays["tmpmap"])
-        quartets = full if full is not None else combinations.random_quartets(proj.nsamples, proj.nqrts, rng)
-
-        q_dev = torch.from_numpy(quartets.view(np.int32))
-        if hasattr(resolver, "device"):
-            q_dev = q_dev.to(resolver.device)
+        if full is not None:
+            quartets, q_dev = full, full_dev
+        elif gpu_index is not None:                                 # same draw as the reference, unranked on the GPU
+            from math import comb
+            ranks = np.random.default_rng(rng).choice(comb(proj.nsamples, 4), size=proj.nqrts, replace=False)
+            q_dev = combinations.device_quartets(proj.nsamples, gpu_index, ranks=ranks)
+            quartets = q_dev.cpu().numpy().view(np.uint32)
+        else:
+            quartets, q_dev = combinations.random_quartets(proj.nsamples, proj.nqrts, rng), None
+        if q_dev is None:
+            q_dev = torch.from_numpy(quartets.view(np.int32))
+            if hasattr(resolver, "device"):
+                q_dev = q_dev.to(resolver.device)
         out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
         if rank == 0:
             rstat, rscor = out
