@@ -260,3 +260,41 @@ def test_device_unranking_matches_itertools_and_reference_vectors(tb):
         cb.device_quartets(10, start=200, count=100)
     with pytest.raises(ValueError):
         cb.device_quartets(10, ranks=np.array([comb(10, 4)]))
+
+
+@pytest.mark.parametrize("sub", [True, False])
+def test_more_than_63_tiles_exercises_the_counter_flush(tb, oracle, sub):
+    """> 64 512 loci = more than 63 tiles of 1024: the packed 16-bit counters are flushed inside the
+    tile loop (as at the C3-C5 shapes).  Exact counts against the oracle."""
+    from tetrad_b200 import synth
+    d = synth.generate(6, 70_000, 150_000, seed=17)
+    db = synth.prepare_database(d.snps, d.snpsmap, seed=17)
+    quartets = np.array([[0, 1, 2, 3], [0, 2, 4, 5], [1, 3, 4, 5], [0, 1, 4, 5], [2, 3, 4, 5]], dtype=np.uint32)
+    eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+    assert eng.info["ntiles"] > 63
+    rstat, rscor, counts, minrank = eng.resolve(quartets, sub, want_counts=True)
+    _, ostat, oscor, det = oracle.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], quartets, sub, return_details=True)
+    assert (counts.cpu().numpy().view(np.uint32).reshape(-1, 16, 16) == det["mats"][:, 0]).all()
+    assert (rstat.cpu().numpy().view(np.uint32) == ostat).all()
+    assert_scores_close(rscor.cpu().numpy(), oscor, ostat[:, 1])
+    assert (minrank.cpu().numpy() == det["minrank"]).all()
+
+
+def test_c3_shape_random_quartets_sampled_parity(tb, oracle):
+    """BASELINE config C3 shape (100 tips, 100 000 loci, 500 000 SNPs): a sample of random quartets,
+    unranked on the device from the reference's rng.choice draw, exact against the oracle."""
+    from math import comb
+    from tetrad_b200 import combinations as cb, synth
+    db = synth.config_arrays("C3")
+    ranks = np.random.default_rng(42).choice(comb(100, 4), size=1_000_000, replace=False)[:3000]
+    q_dev = cb.device_quartets(100, ranks=ranks)
+    eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+    rstat, rscor, counts, minrank = eng.resolve(q_dev, True, want_counts=True)
+    quartets = q_dev.cpu().numpy().view(np.uint32)
+    assert (quartets == cb.unrank_quartets(ranks, 100)).all()
+    pick = np.arange(0, 3000, 25)
+    _, ostat, oscor, det = oracle.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], quartets[pick], True, return_details=True)
+    assert (counts.cpu().numpy().view(np.uint32).reshape(-1, 16, 16)[pick] == det["mats"][:, 0]).all()
+    assert (rstat.cpu().numpy().view(np.uint32)[pick] == ostat).all()
+    assert_scores_close(rscor.cpu().numpy()[pick], oscor, ostat[:, 1])
+    assert (minrank.cpu().numpy()[pick] == det["minrank"]).all()

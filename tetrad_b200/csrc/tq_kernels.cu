@@ -959,13 +959,19 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
 
         double score[3] = {0.001, 0.001, 0.001};                        // :232
         uint32_t best, minrank = 0;
+#ifdef TQ_NO_SVD
+        if (true) {
+#else
         if (nsnps == 0 || (debug & 1u)) {
+#endif
             uint64_t h = seed;
             h = splitmix64(h ^ t.x); h = splitmix64(h ^ t.y);
             h = splitmix64(h ^ t.z); h = splitmix64(h ^ t.w);
             best = (uint32_t)(h % 3ull);                                // stands in for :231
         } else {
+#ifndef TQ_NO_SVD
             svd_scores(ws, lane, score, &best, &minrank, debug);
+#endif
         }
         TQ_ACC(3);
         if (lane == 0) {
