@@ -21,6 +21,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace tq {
 
@@ -29,6 +30,9 @@ int64_t g_launches = 0;
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef TQ_TMEM
 #define TQ_TMEM 1                             // 1: packed pattern counters live in tensor memory (tcgen05.ld/st)
+#endif
+#ifndef TQ_DEFAULT_WS
+#define TQ_DEFAULT_WS 0                       // 1: the warp-specialised kernel is the default (env TQ_KERNEL=ws|fused overrides)
 #endif
 #ifndef TQ_MIN_CTAS
 #define TQ_MIN_CTAS (TQ_TMEM ? 5 : 4)         // resident CTAs per SM the register budget is sized for
@@ -272,14 +276,16 @@ __device__ unsigned long long g_phase_clk[8];
 static constexpr int kStages = 4;               // cp.async ring depth (rank-chunks in flight); 6 was slower (L1 shrinks)
 static constexpr uint32_t kFlushEvery = 63;
 
+struct __align__(16) SvdScratch {
+    double M[3][16][kLdm];                      // flattenings M[m][col][row]; later W (R factor) / exchange buffer
+    double nrm[3][16];                          // singular values
+    double srt[3][16];                          // sorted singular values; pivot-column buffer during the QR
+};
+
 struct __align__(16) WarpScratch {
     union {
         uint4 ring[kStages][4][32];             // stage-1 staging: [stage][tip][lane]      8 KB
-        struct {
-            double M[3][16][kLdm];              // flattenings M[m][col][row]; later the exchange buffer
-            double nrm[3][16];                  // singular values
-            double srt[3][16];
-        } svd;
+        SvdScratch svd;                         // the Jacobi reuses the ring once counting is over
     };
     uint32_t T[256];
 };
@@ -506,7 +512,7 @@ __device__ __noinline__ void flush_tmem(uint32_t tacc, uint32_t *T, int lane)
 
 template <bool kSubsample>
 __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *__restrict__ planes,
-                                              uint4 tips, WarpScratch &ws, int lane, uint32_t debug, uint32_t tacc
+                                              uint4 tips, const uint4 *ring, uint32_t *T, int lane, uint32_t debug, uint32_t tacc
 #ifdef TQ_PHASE_TIMERS
                                               , long long (&ph)[8]
 #endif
@@ -515,19 +521,19 @@ __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *
     TQ_T0();
 #if TQ_TMEM
     const uint32_t acc = tacc;                     // handle of this thread's 64 counters in tensor memory
-#define TQ_FLUSH() flush_tmem(acc, ws.T, lane)
+#define TQ_FLUSH() flush_tmem(acc, T, lane)
 #else
     uint32_t acc[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) acc[i] = 0u;
-#define TQ_FLUSH() flush_acc(acc, ws.T, lane)
+#define TQ_FLUSH() flush_acc(acc, T, lane)
 #endif
     const bool upper = lane >= 16;
     uint32_t pending = 0;
     const uint32_t nchunks = plan.row_u4 / kTileWords;
     const uint32_t t0 = tips.x * plan.row_u4, t1 = tips.y * plan.row_u4;    // row starts, uint4 units
     const uint32_t t2 = tips.z * plan.row_u4, t3 = tips.w * plan.row_u4;
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&ws.ring[0][0][lane]);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + lane);
 
     // prologue: chunks 0 .. kStages-2 in flight
 #pragma unroll
@@ -550,8 +556,8 @@ __device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *
             }
             cp_async_wait<kStages - 1>();
             const int s = u % kStages;
-            const uint4 a = ws.ring[s][0][lane], b = ws.ring[s][1][lane];
-            const uint4 c = ws.ring[s][2][lane], d = ws.ring[s][3][lane];
+            const uint4 *st = ring + s * (4 * 32) + lane;
+            const uint4 a = st[0], b = st[32], c = st[64], d = st[96];
             if (kSubsample && (debug & 4u)) {
                 MA[0] |= a.x; MB[0] |= b.y; MC[0] |= c.z; MD[0] |= d.w;
             } else if (kSubsample) {
@@ -653,15 +659,14 @@ __device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], 
     }
 }
 
-__device__ __noinline__ void svd_scores(WarpScratch &ws, int lane, double *score_out, uint32_t *best_out,
+__device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int lane, double *score_out, uint32_t *best_out,
                                         uint32_t *minrank_out, uint32_t debug)
 {
-    auto &sv = ws.svd;
     double v[8];
     double fro2 = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        v[i] = (double)ws.T[lane + 32 * i];
+        v[i] = (double)T[lane + 32 * i];
         fro2 = fma(v[i], v[i], fro2);
     }
 #pragma unroll
@@ -940,10 +945,10 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
         for (int i = 0; i < 8; ++i) ws.T[lane + 32 * i] = 0u;
         __syncwarp();
 #ifdef TQ_PHASE_TIMERS
-        count_quartet<kSubsample>(plan, planes, t, ws, lane, debug, tacc, ph);
+        count_quartet<kSubsample>(plan, planes, t, &ws.ring[0][0][0], ws.T, lane, debug, tacc, ph);
         long long tq_t0 = clock64();
 #else
-        count_quartet<kSubsample>(plan, planes, t, ws, lane, debug, tacc);
+        count_quartet<kSubsample>(plan, planes, t, &ws.ring[0][0][0], ws.T, lane, debug, tacc);
 #endif
         __syncwarp();
         if (!kSubsample && lane < 4) ws.T[85u * lane] = 0u;   // invariant patterns aaaa, :218
@@ -970,7 +975,7 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
             best = (uint32_t)(h % 3ull);                                // stands in for :231
         } else {
 #ifndef TQ_NO_SVD
-            svd_scores(ws, lane, score, &best, &minrank, debug);
+            svd_scores(ws.T, ws.svd, lane, score, &best, &minrank, debug);
 #endif
         }
         TQ_ACC(3);
@@ -997,6 +1002,176 @@ resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
 #endif
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-specialised variant of the fused kernel.  A CTA has 12 warps: warps 0-7 only count
+// (stage 1 + stage 2, counters in tensor memory, registers trimmed with setmaxnreg), warps 8-11
+// only score (QR + Jacobi, registers raised with setmaxnreg).  Count warp c hands the 256 counts
+// of a quartet to score warp 8 + c/2 through one of two shared-memory slots guarded by a
+// full/empty mbarrier pair, so the POPC-bound and the FP64-latency-bound halves of a quartet run
+// concurrently on different warps instead of back to back on one.  Still one launch; still only
+// scores and the chosen split leave the SM.
+// ------------------------------------------------------------------------------------------
+static constexpr int kWsCount = 8, kWsScore = 4, kWsWarps = kWsCount + kWsScore;
+
+struct __align__(16) WsSlotMeta { long long q; uint4 tips; };
+
+struct __align__(16) WsShared {
+    uint4 ring[kWsCount][kStages][4][32];
+    uint32_t T[kWsCount][2][256];
+    WsSlotMeta meta[kWsCount][2];
+    SvdScratch svd[kWsScore];
+    unsigned long long full[kWsCount][2], empty[kWsCount][2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n}\n"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// Wait for the phase with the given parity to complete.  A wait that lasts seconds means a protocol
+// bug: trap (launch error) rather than hang the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 20000000000ll) __trap();
+    }
+}
+
+template <bool kSubsample>
+__global__ void __launch_bounds__(kWsWarps * 32, 2)
+resolve_ws_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
+                  const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
+                  double *__restrict__ rscor, uint2 *__restrict__ rstat,
+                  uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
+                  uint32_t *__restrict__ status)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WsShared &sh = *reinterpret_cast<WsShared *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < kWsCount; ++c)
+            for (int b = 0; b < 2; ++b) { mbar_init(&sh.full[c][b], 1); mbar_init(&sh.empty[c][b], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&sh.tmem_base);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(slot), "r"(2 * kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = sh.tmem_base;
+
+    const int64_t ncount = (int64_t)gridDim.x * kWsCount;               // count warps in the grid
+    auto quartets_of = [&](int c) -> int64_t {                           // how many quartets count warp c of this CTA resolves
+        const int64_t first = (int64_t)blockIdx.x * kWsCount + c;
+        return first < m ? (m - first + ncount - 1) / ncount : 0;
+    };
+
+    if (warp < kWsCount) {
+        // ------------------------------ count warps ------------------------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+        const int c = warp;
+        const uint32_t tacc = tmem_base + ((uint32_t)((c & 3) * 32) << 16) + (uint32_t)(c >> 2) * kTmemCols;
+        zero_acc(tacc);
+        const int64_t n = quartets_of(c);
+        int64_t q = (int64_t)blockIdx.x * kWsCount + c;
+        for (int64_t it = 0; it < n; ++it, q += ncount) {
+            const int b = (int)(it & 1);
+            mbar_wait(&sh.empty[c][b], (uint32_t)(((it >> 1) & 1) ^ 1));   // slot free (passes at once the first time)
+            uint32_t *T = sh.T[c][b];
+            const uint4 t = __ldg(quartets + q);
+            const bool bad = t.x >= ntips || t.y >= ntips || t.z >= ntips || t.w >= ntips;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
+            __syncwarp();
+            if (!bad) count_quartet<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], T, lane, 0u, tacc);
+            if (lane == 0) { sh.meta[c][b].q = bad ? -1 - q : q; sh.meta[c][b].tips = t; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.full[c][b]);
+        }
+        tmem_wait_st();
+    } else {
+        // ------------------------------ score warps ------------------------------
+        // pool = 384 threads x 80 registers (ptxas, launch bounds (384, 2)); 256 x 72 + 128 x 96 uses it exactly.
+        // Asking for more than the pool holds would wait forever.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;\n");
+        const int sidx = warp - kWsCount;
+        SvdScratch &sv = sh.svd[sidx];
+        const int c0 = 2 * sidx;
+        const int64_t n0 = quartets_of(c0), n1 = quartets_of(c0 + 1);
+        const int64_t nmax = n0 > n1 ? n0 : n1;
+        for (int64_t it = 0; it < nmax; ++it) {
+            const int b = (int)(it & 1);
+            const uint32_t parity = (uint32_t)((it >> 1) & 1);
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+                const int c = c0 + k;
+                if (it >= (k ? n1 : n0)) continue;
+                mbar_wait(&sh.full[c][b], parity);
+                uint32_t *T = sh.T[c][b];
+                const long long mq = sh.meta[c][b].q;
+                const uint4 t = sh.meta[c][b].tips;
+                if (mq < 0) {                                              // tip index out of range
+                    const long long q = -1 - mq;
+                    if (lane == 0) {
+                        rstat[q] = make_uint2(0xFFFFFFFFu, 0u);
+                        rscor[3 * q] = rscor[3 * q + 1] = rscor[3 * q + 2] = 0.0;
+                        if (status) atomicOr(status, 1u);
+                    }
+                } else {
+                    const long long q = mq;
+                    if (!kSubsample && lane < 4) T[85u * lane] = 0u;      // invariant patterns aaaa, :218
+                    __syncwarp();
+                    uint32_t nsnps = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t v = T[lane + 32 * i];
+                        nsnps += v;
+                        if (counts) counts[q * 256 + lane + 32 * i] = v;
+                    }
+                    nsnps = __reduce_add_sync(kFull, nsnps);                // :226
+                    double score[3] = {0.001, 0.001, 0.001};                // :232
+                    uint32_t best, minrank = 0;
+                    if (nsnps == 0) {
+                        uint64_t h = seed;
+                        h = splitmix64(h ^ t.x); h = splitmix64(h ^ t.y);
+                        h = splitmix64(h ^ t.z); h = splitmix64(h ^ t.w);
+                        best = (uint32_t)(h % 3ull);                        // stands in for :231
+                    } else {
+                        svd_scores(T, sv, lane, score, &best, &minrank, 0u);
+                    }
+                    if (lane == 0) {
+                        rscor[3 * q] = score[0]; rscor[3 * q + 1] = score[1]; rscor[3 * q + 2] = score[2];
+                        rstat[q] = make_uint2(best, nsnps);                 // :251, :264
+                        if (minrank_out) minrank_out[q] = minrank;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.empty[c][b]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * kTmemCols) : "memory");
+}
+
 cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips,
                            const uint32_t *d_quartets, int64_t m, bool subsample, uint64_t seed,
                            double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
@@ -1017,6 +1192,27 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     const uint4 *planes = reinterpret_cast<const uint4 *>(d_planes);
     const uint4 *quartets = reinterpret_cast<const uint4 *>(d_quartets);
     uint2 *rstat = reinterpret_cast<uint2 *>(d_rstat);
+    static const bool use_ws = getenv("TQ_KERNEL") ? (strcmp(getenv("TQ_KERNEL"), "ws") == 0) : (TQ_DEFAULT_WS != 0);
+    if (use_ws && TQ_TMEM) {
+        const size_t wsmem = sizeof(WsShared);
+        static bool ws_attr = false;
+        if (!ws_attr) {
+            cudaFuncSetAttribute(resolve_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+            cudaFuncSetAttribute(resolve_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+            ws_attr = true;
+        }
+        const int64_t wwant = (m + kWsCount - 1) / kWsCount;
+        const int64_t wcap = (int64_t)num_sms * 2;
+        const unsigned wgrid = (unsigned)(wwant < wcap ? wwant : wcap);
+        if (subsample)
+            resolve_ws_kernel<true><<<wgrid, kWsWarps * 32, wsmem, stream>>>(plan, planes, (uint32_t)ntips, quartets, m, seed,
+                                                                            d_rscor, rstat, d_counts, d_minrank, d_status);
+        else
+            resolve_ws_kernel<false><<<wgrid, kWsWarps * 32, wsmem, stream>>>(plan, planes, (uint32_t)ntips, quartets, m, seed,
+                                                                             d_rscor, rstat, d_counts, d_minrank, d_status);
+        ++g_launches;
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(WarpScratch) * kWarps;
     static bool attr_set = false;
     if (!attr_set) {
