@@ -282,8 +282,12 @@ def run_ours(args):
     prof = ROOT / "profiles" / "resolve_traffic.json"
     if prof.exists():
         traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    forced = os.environ.get("TQ_KERNEL")
+    specialised = (forced == "ws") if forced else Q >= sms * 64      # same rule as launch_resolve (tq_kernels.cu)
     roofline = {
-        "bound": "hbm", "kernel": "tq::resolve_kernel<true>", "achieved": achieved, "peak": peak_gbs,
+        "bound": "hbm", "kernel": "tq::resolve_ws_kernel<true>" if specialised else "tq::resolve_kernel<true>",
+        "achieved": achieved, "peak": peak_gbs,
         "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_quartet": algorithmic_bytes_per_quartet(meta["ncols"]),
         "kernel_ms": statistics.mean(kern_ms),

@@ -31,8 +31,12 @@ static constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef TQ_TMEM
 #define TQ_TMEM 1                             // 1: packed pattern counters live in tensor memory (tcgen05.ld/st)
 #endif
+#ifndef TQ_WS_DEC
+#define TQ_WS_DEC 72                          // registers of a count warp in the warp-specialised kernel
+#define TQ_WS_INC 96                          // registers of a score warp; 256*DEC + 128*INC must equal 384*80
+#endif
 #ifndef TQ_DEFAULT_WS
-#define TQ_DEFAULT_WS 0                       // 1: the warp-specialised kernel is the default (env TQ_KERNEL=ws|fused overrides)
+#define TQ_DEFAULT_WS 1                       // 1: large launches use the warp-specialised kernel (env TQ_KERNEL=ws|fused overrides)
 #endif
 #ifndef TQ_MIN_CTAS
 #define TQ_MIN_CTAS (TQ_TMEM ? 5 : 4)         // resident CTAs per SM the register budget is sized for
@@ -1084,7 +1088,7 @@ resolve_ws_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips
 
     if (warp < kWsCount) {
         // ------------------------------ count warps ------------------------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(TQ_WS_DEC));
         const int c = warp;
         const uint32_t tacc = tmem_base + ((uint32_t)((c & 3) * 32) << 16) + (uint32_t)(c >> 2) * kTmemCols;
         zero_acc(tacc);
@@ -1109,7 +1113,7 @@ resolve_ws_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips
         // ------------------------------ score warps ------------------------------
         // pool = 384 threads x 80 registers (ptxas, launch bounds (384, 2)); 256 x 72 + 128 x 96 uses it exactly.
         // Asking for more than the pool holds would wait forever.
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;\n");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(TQ_WS_INC));
         const int sidx = warp - kWsCount;
         SvdScratch &sv = sh.svd[sidx];
         const int c0 = 2 * sidx;
@@ -1192,7 +1196,11 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     const uint4 *planes = reinterpret_cast<const uint4 *>(d_planes);
     const uint4 *quartets = reinterpret_cast<const uint4 *>(d_quartets);
     uint2 *rstat = reinterpret_cast<uint2 *>(d_rstat);
-    static const bool use_ws = getenv("TQ_KERNEL") ? (strcmp(getenv("TQ_KERNEL"), "ws") == 0) : (TQ_DEFAULT_WS != 0);
+    // Two variants of the same fused kernel.  With enough quartets to keep every warp busy for many
+    // iterations the warp-specialised one wins (C2: 7.67 vs 7.31 M quartets/s); on tiny launches
+    // (C1: 495 quartets) its count -> score hand-off is pure latency.  TQ_KERNEL=ws|fused overrides.
+    static const char *force = getenv("TQ_KERNEL");
+    const bool use_ws = force ? (strcmp(force, "ws") == 0) : (TQ_DEFAULT_WS != 0 && m >= (int64_t)num_sms * 64);
     if (use_ws && TQ_TMEM) {
         const size_t wsmem = sizeof(WsShared);
         static bool ws_attr = false;
