@@ -152,6 +152,21 @@ int tq_resolve_host(tq_ctx *ctx,
 int tq_ctx_last_traffic(const tq_ctx *ctx, int64_t out[2]);
 
 /* ------------------------------------------------------------------------------------------
+ * Result sink (host only, no CUDA): the text the reference writes with pandas / per-line Python.
+ * tq_format_tsv: rows "t0 t1 t2 t3 s0 s1 s2 best nsnps" (tab separated, scores %.6f, '\n' ended) of
+ *   {name}.quartets_{rep}.tsv (run_inference.py:232-234) into `out`; returns the number of bytes
+ *   written, TQ_ENOMEM if `cap` (>= 160 bytes per row suffices) is too small.
+ * tq_round_scores: every score as it reads back from that text (the reference derives its wQMC weights
+ *   from the parsed TSV, run_inference.py:262-297).
+ * tq_format_qmc: lines "a,b|c,d:%.5f" (run_inference.py:305) for n quartets whose tips are already in
+ *   split order; returns bytes written (>= 128 bytes per line suffices).
+ */
+int64_t tq_format_tsv(const uint32_t *quartets, const uint32_t *rstat, const double *rscor, int64_t m,
+                      char *out, int64_t cap);
+int     tq_round_scores(const double *rscor, int64_t n, double *out);
+int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, char *out, int64_t cap);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): pipe micro-benchmarks on `device`.
  * kind 0: POPC  (result: popc32 thread-instructions per second)
  * kind 1: LOP3  (and/or)      kind 2: DFMA        kind 3: device copy (bytes/s, read+write)

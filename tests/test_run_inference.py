@@ -40,6 +40,48 @@ def test_write_qmc_format_is_a_seeded_permutation(tmp_path):
     assert a.splitlines() != str(sink["w1"]).splitlines()
 
 
+def test_in_memory_sink_equals_file_based_sink(tmp_path):
+    """The C sink fed from memory (what the replicate loop does) writes the same wQMC input as the
+    reference-style path that re-reads the TSV, for every weighting and filter."""
+    g = load_golden("noisy12")
+    f = tmp_path / "q.tsv"
+    run_inference.write_quartets_tsv(f, g["quartets"], g["sub_rstat"], g["sub_rscor"])
+    res = (g["quartets"], g["sub_rstat"], g["sub_rscor"])
+    for kw in (dict(weights=0), dict(weights=1), dict(weights=2), dict(weights=3), dict(weights=1, min_snps=400),
+               dict(weights=2, min_ratio=5.0)):
+        tips, weight = run_inference.qmc_weights(*res, **kw)
+        text = run_inference.format_qmc_lines(tips, weight).decode()
+        assert text == "".join(line + "\n" for line in run_inference.iter_qmc_formatted(f, **kw))
+        run_inference.write_qmc_format(f, tmp_path / "a.txt", rng=5, **kw)
+        run_inference.write_qmc_format(f, tmp_path / "b.txt", rng=5, results=res, **kw)
+        assert (tmp_path / "a.txt").read_bytes() == (tmp_path / "b.txt").read_bytes()
+
+
+def test_c_formatter_rounds_like_printf(tmp_path):
+    """%.6f / %.5f ties, carries, tiny, huge and non-finite values: byte-identical to Python's
+    (= the C library's) formatting, and the read-back value equals float(text)."""
+    import ctypes
+    from tetrad_b200 import _lib
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.random(20000) * 10.0 ** rng.integers(-8, 7, 20000), (rng.integers(0, 10**9, 20000) + 0.5) / 1e6,
+                           np.arange(2000) / 64.0 + 0.0000005, [0.0, 0.001, 0.9999995, 0.9999994999, 1e-7, 5e-7, 123456789.123456789,
+                                                               2.5e-6, 3.9e9, 4.1e9, 1e15]])
+    vals = vals[: len(vals) // 3 * 3].reshape(-1, 3)
+    m = len(vals)
+    q = np.zeros((m, 4), np.uint32); st = np.zeros((m, 2), np.uint32)
+    f = tmp_path / "v.tsv"
+    run_inference.write_quartets_tsv(f, q, st, vals)
+    got = [line.split("\t")[4:7] for line in f.read_text().splitlines()]
+    want = [["%.6f" % x for x in row] for row in vals]
+    assert got == want
+    back = np.empty_like(vals)
+    assert _lib.load().tq_round_scores(vals.ctypes.data, vals.size, back.ctypes.data) == 0
+    assert (back == np.array([[float(x) for x in row] for row in want])).all()
+    w = np.ascontiguousarray(vals[:, 0])
+    lines = run_inference.format_qmc_lines(np.zeros((m, 4), np.uint32), w).decode().splitlines()
+    assert lines == ["0,0|0,0:%.5f" % x for x in w]
+
+
 def test_relabel_tree():
     names = {0: "a", 1: "b_1", 2: "c", 3: "d", 10: "k"}
     assert run_inference.relabel_tree("((0,1),(2,(3,10)));\n", names) == "((a,b_1),(c,(d,k)));"

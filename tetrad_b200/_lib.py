@@ -14,7 +14,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 _ROOT = _PKG.parent
 LIB_PATH = _PKG / "libtetrad_b200.so"
-SOURCES = [_PKG / "csrc" / "tq_kernels.cu", _PKG / "csrc" / "tq_api.cu"]
+SOURCES = [_PKG / "csrc" / "tq_kernels.cu", _PKG / "csrc" / "tq_api.cu", _PKG / "csrc" / "tq_sink.cpp"]
 HEADERS = [_PKG / "csrc" / "tq_kernels.cuh", _ROOT / "include" / "tetrad_b200.h"]
 
 NVCC_FLAGS = [
@@ -85,6 +85,12 @@ def _declare(lib):
     lib.tq_plan_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.tq_plan_create_runs.restype = i32
     lib.tq_plan_create_runs.argtypes = [vp, i64, i32, vp, c.POINTER(vp)]
+    lib.tq_format_tsv.restype = i64
+    lib.tq_format_tsv.argtypes = [vp, vp, vp, i64, vp, i64]
+    lib.tq_round_scores.restype = i32
+    lib.tq_round_scores.argtypes = [vp, i64, vp]
+    lib.tq_format_qmc.restype = i64
+    lib.tq_format_qmc.argtypes = [vp, vp, i64, vp, i64]
     lib.tq_unrank.restype = i32
     lib.tq_unrank.argtypes = [i32, vp, i64, i64, i64, vp, vp]
     lib.tq_boot_pack.restype = i32
@@ -109,7 +115,7 @@ EXPORTS = [
     "tq_version", "tq_last_error", "tq_launch_count", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
     "tq_plan_destroy",
     "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
-    "tq_ctx_last_traffic", "tq_microbench",
+    "tq_ctx_last_traffic", "tq_microbench", "tq_format_tsv", "tq_round_scores", "tq_format_qmc",
 ]
 
 

@@ -35,6 +35,9 @@ static constexpr unsigned kFull = 0xFFFFFFFFu;
 #define TQ_WS_DEC 72                          // registers of a count warp in the warp-specialised kernel
 #define TQ_WS_INC 96                          // registers of a score warp; 256*DEC + 128*INC must equal 384*80
 #endif
+#ifndef TQ_ROWS_IN_FLIGHT
+#define TQ_ROWS_IN_FLIGHT 2                    // pattern rows (16 POPCs each) kept in flight in stage 2
+#endif
 #ifndef TQ_DEFAULT_WS
 #define TQ_DEFAULT_WS 1                       // 1: large launches use the warp-specialised kernel (env TQ_KERNEL=ws|fused overrides)
 #endif
@@ -398,6 +401,7 @@ __device__ __forceinline__ void count_tile(const uint32_t (&MA)[4], const uint32
         const uint32_t a_own = (g >> 1) ? A1 : A0, a_par = (g >> 1) ? pA1 : pA0;
         const uint32_t o0 = a_own & (hi ? MB[2] : MB[0]), o1 = a_own & (hi ? MB[3] : MB[1]);
         const uint32_t q0 = a_par & (hi ? pB[2] : pB[0]), q1 = a_par & (hi ? pB[3] : pB[1]);
+#if TQ_ROWS_IN_FLIGHT == 2
         uint32_t va[16], vb[16];
         row_and(o0, MC, MD, va);
         row_popc(va);
@@ -412,6 +416,15 @@ __device__ __forceinline__ void count_tile(const uint32_t (&MA)[4], const uint32
         row_add(va, acc);
         row_popc(vb);
         row_add(vb, acc + 8);
+#else
+        uint32_t va[16];
+        row_and(o0, MC, MD, va); row_popc(va);
+        tmem_wait_ld();
+        row_add(va, acc);
+        row_and(o1, MC, MD, va); row_popc(va); row_add(va, acc + 8);
+        row_and(q0, pC, pD, va); row_popc(va); row_add(va, acc);
+        row_and(q1, pC, pD, va); row_popc(va); row_add(va, acc + 8);
+#endif
         tmem_st16(tacc + 16 * g, acc);
     }
 }

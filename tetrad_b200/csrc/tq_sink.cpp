@@ -1,0 +1,126 @@
+// Host-side result sink of the hot path (no CUDA): the text the reference produces with pandas
+// and per-line Python, formatted in C.
+//   tq_format_tsv    rows of {name}.quartets_{rep}.tsv   (tetrad/src/run_inference.py:232-234)
+//   tq_round_scores  the value each score has after a trip through that text (the reference computes
+//                    its wQMC weights from the parsed TSV, run_inference.py:262-297)
+//   tq_format_qmc    lines "a,b|c,d:weight" of the wQMC input (run_inference.py:305)
+#include "../../include/tetrad_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+// x >= 0 rounded to `digits` decimals exactly as printf("%.*f") does, returned as the integer
+// N = round(x * 10^digits).  Fast path: scale and round; when the scaled value is too close to a
+// rounding boundary for double arithmetic to be trusted (or too large), let snprintf decide.
+bool scaled_round(double x, int digits, unsigned long long *out)
+{
+    static const double pow10[] = {1, 10, 100, 1000, 10000, 100000, 1000000};
+    if (!(x >= 0.0) || x >= 4.0e9) return false;
+    const double ip = std::floor(x);
+    const double t = (x - ip) * pow10[digits];            // x - ip is exact; the product has one rounding
+    const double ft = std::floor(t);
+    const double d = t - ft;
+    if (std::fabs(d - 0.5) < 1e-5) return false;          // near a tie: exact decimal expansion needed
+    unsigned long long frac = (unsigned long long)ft + (d > 0.5 ? 1ull : 0ull);
+    unsigned long long whole = (unsigned long long)ip;
+    const unsigned long long scale = (unsigned long long)pow10[digits];
+    if (frac >= scale) { frac -= scale; whole += 1; }
+    *out = whole * scale + frac;
+    return true;
+}
+
+unsigned long long exact_round(double x, int digits)
+{
+    unsigned long long n;
+    if (scaled_round(x, digits, &n)) return n;
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%.*f", digits, x);        // correctly rounded by the C library
+    unsigned long long whole = 0, frac = 0;
+    const char *p = buf;
+    while (*p >= '0' && *p <= '9') whole = whole * 10 + (unsigned)(*p++ - '0');
+    if (*p == '.') ++p;
+    while (*p >= '0' && *p <= '9') frac = frac * 10 + (unsigned)(*p++ - '0');
+    unsigned long long scale = 1;
+    for (int i = 0; i < digits; ++i) scale *= 10;
+    return whole * scale + frac;
+}
+
+inline char *put_uint(char *p, unsigned long long v)
+{
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+inline char *put_fixed(char *p, unsigned long long scaled, int digits)
+{
+    unsigned long long scale = 1;
+    for (int i = 0; i < digits; ++i) scale *= 10;
+    p = put_uint(p, scaled / scale);
+    *p++ = '.';
+    unsigned long long frac = scaled % scale;
+    for (unsigned long long s = scale / 10; s; s /= 10) { *p++ = (char)('0' + frac / s); frac %= s; }
+    return p;
+}
+
+bool printable(double x) { return x >= 0.0 && x < 4.0e9; }   // NaN / inf / negative: not a score
+
+}  // namespace
+
+extern "C" {
+
+int64_t tq_format_tsv(const uint32_t *quartets, const uint32_t *rstat, const double *rscor, int64_t m,
+                      char *out, int64_t cap)
+{
+    if (m < 0 || (m > 0 && (!quartets || !rstat || !rscor || !out))) return TQ_EINVAL;
+    char *p = out;
+    for (int64_t i = 0; i < m; ++i) {
+        if (cap - (p - out) < 160) return TQ_ENOMEM;      // longest possible row is < 160 bytes
+        for (int k = 0; k < 4; ++k) { p = put_uint(p, quartets[4 * i + k]); *p++ = '\t'; }
+        for (int k = 0; k < 3; ++k) {
+            const double x = rscor[3 * i + k];
+            if (printable(x)) p = put_fixed(p, exact_round(x, 6), 6);
+            else p += snprintf(p, 64, "%.6f", x);
+            *p++ = '\t';
+        }
+        p = put_uint(p, rstat[2 * i]); *p++ = '\t';
+        p = put_uint(p, rstat[2 * i + 1]); *p++ = '\n';
+    }
+    return (int64_t)(p - out);
+}
+
+int tq_round_scores(const double *rscor, int64_t n, double *out)
+{
+    if (n < 0 || (n > 0 && (!rscor || !out))) return TQ_EINVAL;
+    for (int64_t i = 0; i < n; ++i) {
+        const double x = rscor[i];
+        // N / 10^6 with N < 2^53 is the correctly rounded value of the decimal text, i.e. what strtod returns
+        out[i] = printable(x) ? (double)exact_round(x, 6) / 1.0e6 : x;
+    }
+    return TQ_OK;
+}
+
+int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, char *out, int64_t cap)
+{
+    if (n < 0 || (n > 0 && (!tips || !weight || !out))) return TQ_EINVAL;
+    char *p = out;
+    for (int64_t i = 0; i < n; ++i) {
+        if (cap - (p - out) < 128) return TQ_ENOMEM;
+        p = put_uint(p, tips[4 * i]); *p++ = ',';
+        p = put_uint(p, tips[4 * i + 1]); *p++ = '|';
+        p = put_uint(p, tips[4 * i + 2]); *p++ = ',';
+        p = put_uint(p, tips[4 * i + 3]); *p++ = ':';
+        const double w = weight[i];
+        if (printable(w)) p = put_fixed(p, exact_round(w, 5), 5);
+        else p += snprintf(p, 64, "%.5f", w);
+        *p++ = '\n';
+    }
+    return (int64_t)(p - out);
+}
+
+}  // extern "C"

@@ -65,13 +65,70 @@ def resample_arrays(seqarr: np.ndarray, spans: np.ndarray, rng: np.random.Genera
 # ----------------------------------------------------------------------------------------------
 def write_quartets_tsv(path: Path, quartets, rstat, rscor, append: bool = False) -> None:
     """``t0 t1 t2 t3 s0 s1 s2 best nsnps``, tab-separated, scores ``%.6f``, no header: the line
-    format pandas produces at run_inference.py:232-234."""
-    table = np.empty((len(quartets), 9), dtype=np.float64)
-    table[:, 0:4] = quartets
-    table[:, 4:7] = rscor
-    table[:, 7:9] = rstat
-    with open(path, "a" if append else "w") as out:
-        np.savetxt(out, table, fmt="%d\t%d\t%d\t%d\t%.6f\t%.6f\t%.6f\t%d\t%d")
+    format pandas produces at run_inference.py:232-234.  Formatted in C (``tq_format_tsv``)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    quartets = np.ascontiguousarray(quartets, dtype=np.uint32).reshape(-1, 4)
+    rstat = np.ascontiguousarray(rstat, dtype=np.uint32).reshape(-1, 2)
+    rscor = np.ascontiguousarray(rscor, dtype=np.float64).reshape(-1, 3)
+    step = 1 << 17
+    buf = ctypes.create_string_buffer(160 * min(step, max(1, len(quartets))))
+    with open(path, "ab" if append else "wb") as out:
+        for lo in range(0, len(quartets), step):
+            q, st, sc = quartets[lo: lo + step], rstat[lo: lo + step], rscor[lo: lo + step]
+            n = lib.tq_format_tsv(q.ctypes.data, st.ctypes.data, sc.ctypes.data, len(q), buf, len(buf))
+            if n < 0:
+                _lib.check(int(n))
+            out.write(buf.raw[:n])
+
+
+def qmc_weights(quartets, rstat, rscor, weights: int, min_snps: int = 0, min_ratio: float = 1.0):
+    """In-memory twin of ``iter_qmc_formatted``: (tips u32[n,4] in split order, weight f64[n]) of the
+    quartets that pass the filters.  Scores are first rounded through the TSV's ``%.6f`` text
+    (``tq_round_scores``) because the reference computes its weights from the parsed file."""
+    from . import _lib
+    if weights not in (0, 1, 2, 3):
+        raise ValueError(f"no weight strategy {weights}")
+    lib = _lib.load()
+    quartets = np.ascontiguousarray(quartets, dtype=np.uint32).reshape(-1, 4)
+    rstat = np.ascontiguousarray(rstat, dtype=np.uint32).reshape(-1, 2)
+    rscor = np.ascontiguousarray(rscor, dtype=np.float64).reshape(-1, 3)
+    scores = np.empty_like(rscor)
+    _lib.check(lib.tq_round_scores(rscor.ctypes.data, rscor.size, scores.ctypes.data))
+    min_snps = max(1, min_snps)
+    best = np.minimum(rstat[:, 0].astype(np.int64), 2)
+    tips = np.take_along_axis(quartets, TIDXS[best].astype(np.int64), axis=1)
+    srt = np.sort(scores, axis=1)
+    if not weights:
+        weight = np.ones(len(quartets))
+        ratio = np.ones(len(quartets))
+    else:
+        smean = srt[:, 1:].mean(axis=1)
+        smin = srt[:, 0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = np.where(smin == 0, 1.0, smean / np.where(smin == 0, 1.0, smin))
+            third = 1.0 - smin / srt.sum(axis=1)
+        weight = {1: smean, 2: ratio, 3: third}[weights]
+    keep = (rstat[:, 1] >= min_snps) & ~(ratio < min_ratio)
+    return np.ascontiguousarray(tips[keep], dtype=np.uint32), np.ascontiguousarray(weight[keep], dtype=np.float64)
+
+
+def format_qmc_lines(tips: np.ndarray, weight: np.ndarray) -> bytes:
+    """``a,b|c,d:%.5f`` lines (run_inference.py:305), formatted in C (``tq_format_qmc``)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    out, step = [], 1 << 17
+    buf = ctypes.create_string_buffer(128 * min(step, max(1, len(tips))))
+    for lo in range(0, len(tips), step):
+        t = np.ascontiguousarray(tips[lo: lo + step], dtype=np.uint32)
+        w = np.ascontiguousarray(weight[lo: lo + step], dtype=np.float64)
+        n = lib.tq_format_qmc(t.ctypes.data, w.ctypes.data, len(t), buf, len(buf))
+        if n < 0:
+            _lib.check(int(n))
+        out.append(buf.raw[:n])
+    return b"".join(out)
 
 
 def read_quartets_tsv(path: Path):
@@ -109,14 +166,18 @@ def iter_qmc_formatted(qrts_file: Path, weights: int, min_snps: int = 0, min_rat
 
 
 def write_qmc_format(qrts_file: Path, qmc_in_file: Path, weights: int = 0, min_snps: int = 0,
-                     min_ratio: float = 1.0, rng=None) -> int:
+                     min_ratio: float = 1.0, rng=None, results=None) -> int:
     """Write the weighted quartets in random order (reference :308-327; the reference shells out
-    to ``shuf``, which cannot be seeded -- here the order comes from ``rng``)."""
-    lines = list(iter_qmc_formatted(qrts_file, weights, min_snps, min_ratio))
-    perm = np.random.default_rng(rng).permutation(len(lines))
-    with open(qmc_in_file, "w") as out:
-        out.write("".join(lines[i] + "\n" for i in perm))
-    return len(lines)
+    to ``shuf``, which cannot be seeded -- here the order comes from ``rng``).  ``results`` =
+    (quartets, rstat, rscor) still in memory skips re-reading the TSV; the output is identical."""
+    if results is None:
+        quartets, scores, best, nsnps = read_quartets_tsv(qrts_file)
+        results = (quartets, np.stack([best, nsnps], axis=1), scores)
+    tips, weight = qmc_weights(*results, weights, min_snps, min_ratio)
+    perm = np.random.default_rng(rng).permutation(len(tips))
+    with open(qmc_in_file, "wb") as out:
+        out.write(format_qmc_lines(tips[perm], weight[perm]))
+    return len(tips)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -154,7 +215,7 @@ def relabel_tree(newick: str, samples: dict) -> str:
 
 
 def infer_supertree(proj: Project, idx: int, weights: int, min_snps: int = 0, min_ratio: float = 1.0,
-                    rng=None):
+                    rng=None, results=None):
     """Quartet supertree of replicate ``idx`` as newick, or None without a wQMC binary.  Unlike the
     reference (:337-351) the tree that is relabelled is the one wQMC wrote for THIS replicate."""
     qrts_file = proj.workdir / f"{proj.name}.quartets_{idx}.tsv"
@@ -163,7 +224,7 @@ def infer_supertree(proj: Project, idx: int, weights: int, min_snps: int = 0, mi
         qmc_out = proj.qmc_out_file.parent / f"tmp_out{idx}"
     else:
         qmc_in, qmc_out = proj.qmc_in_file, proj.qmc_out_file
-    write_qmc_format(qrts_file, qmc_in, weights, min_snps, min_ratio, rng=rng)
+    write_qmc_format(qrts_file, qmc_in, weights, min_snps, min_ratio, rng=rng, results=results)
     if get_qmc_bin() is None:
         logger.warning("wQMC binary not found: quartets written, supertree skipped")
         return None
@@ -248,8 +309,10 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
         out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
         if rank == 0:
             rstat, rscor = out
-            write_quartets_tsv(proj.qrts_file, quartets, rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy())
-            nwk = infer_supertree(proj, proj.bootstrap_idx, proj.weights, rng=proj.bootstrap_idx)
+            rstat, rscor = rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy()
+            write_quartets_tsv(proj.qrts_file, quartets, rstat, rscor)
+            nwk = infer_supertree(proj, proj.bootstrap_idx, proj.weights, rng=proj.bootstrap_idx,
+                                  results=(quartets, rstat, rscor))
             if nwk is not None:
                 if proj.bootstrap_idx == 0:
                     proj.best_file.write_text(nwk + "\n")
