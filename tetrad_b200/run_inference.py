@@ -248,7 +248,7 @@ def draw_bootstrap(spans: np.ndarray, rng: np.random.Generator):
 
 
 def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int = 0, resolver=None,
-                  device_bootstrap: bool = True) -> None:
+                  device_bootstrap: bool = True, overlap_sink: bool = True) -> None:
     """Resolve replicate 0 (original data) and ``nboots`` bootstrap replicates, checkpointing
     after each one exactly like the reference (:405-407).  ``ncores`` is accepted for CLI
     compatibility and ignored: the work runs on the GPU(s).  ``resolver`` (tests) overrides the
@@ -273,6 +273,9 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
         logger.info("continuing quartet tree inference")
         rng = proj.bootstrap_rng.to_rng()
 
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=1) if overlap_sink else None
+    pending = None
     exhaustive = proj.nqrts == proj.nqrts_total
     gpu_index = getattr(getattr(resolver, "device", None), "index", None)      # None for CPU stand-ins (tests)
     full = full_dev = None
@@ -307,20 +310,39 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
             if hasattr(resolver, "device"):
                 q_dev = q_dev.to(resolver.device)
         out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
+        idx = proj.bootstrap_idx
+        rng_state = RNGStateModel.from_rng(rng)          # generator state after this replicate's draws
+        if pending is not None:
+            pending.result()                               # sinks finish (and checkpoint) in replicate order
+            pending = None
         if rank == 0:
             rstat, rscor = out
-            rstat, rscor = rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy()
-            write_quartets_tsv(proj.qrts_file, quartets, rstat, rscor)
-            nwk = infer_supertree(proj, proj.bootstrap_idx, proj.weights, rng=proj.bootstrap_idx,
-                                  results=(quartets, rstat, rscor))
-            if nwk is not None:
-                if proj.bootstrap_idx == 0:
-                    proj.best_file.write_text(nwk + "\n")
-                else:
-                    with open(proj.boots_file, "a") as outfh:
-                        outfh.write(nwk + "\n")
-        logger.info(f"finished rep {proj.bootstrap_idx}")
+            # D2H here (the GPU is idle anyway until the next launch); formatting, wQMC and the
+            # checkpoint run on a worker thread while the next replicate is resolved
+            job = (idx, quartets, rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy(), rng_state)
+            pending = pool.submit(_sink_replicate, proj, *job) if pool is not None else _sink_replicate(proj, *job)
+            if pool is None:
+                pending = None
+        logger.info(f"finished rep {idx}")
         proj.bootstrap_idx += 1
-        proj.bootstrap_rng = RNGStateModel.from_rng(rng)
-        if rank == 0:
-            proj.save_json()
+        proj.bootstrap_rng = rng_state
+    if pending is not None:
+        pending.result()
+    if pool is not None:
+        pool.shutdown()
+
+
+def _sink_replicate(proj: Project, idx: int, quartets, rstat, rscor, rng_state) -> None:
+    """Everything that happens to a replicate's results on the host: TSV, wQMC input, supertree,
+    tree files, and the JSON checkpoint that makes the replicate durable (reference :396-407)."""
+    snap = proj.model_copy(update=dict(bootstrap_idx=idx))
+    write_quartets_tsv(snap.qrts_file, quartets, rstat, rscor)
+    nwk = infer_supertree(snap, idx, proj.weights, rng=idx, results=(quartets, rstat, rscor))
+    if nwk is not None:
+        if idx == 0:
+            proj.best_file.write_text(nwk + "\n")
+        else:
+            with open(proj.boots_file, "a") as outfh:
+                outfh.write(nwk + "\n")
+    done = proj.model_copy(update=dict(bootstrap_idx=idx + 1, bootstrap_rng=rng_state))
+    done.save_json()
