@@ -227,6 +227,8 @@ def infer_supertree(proj: Project, idx: int, weights: int, min_snps: int = 0, mi
     write_qmc_format(qrts_file, qmc_in, weights, min_snps, min_ratio, rng=rng, results=results)
     if get_qmc_bin() is None:
         logger.warning("wQMC binary not found: quartets written, supertree skipped")
+        if idx:
+            qmc_in.unlink()          # bootstrap inputs are temporary in the reference too (:353-356)
         return None
     run_qmc(qmc_in, qmc_out, bool(weights))
     nwk = relabel_tree(Path(qmc_out).read_text(), proj.samples)
@@ -284,7 +286,9 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
         full = full_dev.cpu().numpy().view(np.uint32)
     elif exhaustive:
         full = combinations.all_quartets(proj.nsamples)
+    import time
     while proj.bootstrap_idx <= nboots:
+        t_start = time.perf_counter()
         # the reference's quartet generator is lazy: its draw happens after the resampling draws
         on_device = device_bootstrap and hasattr(resolver, "load_bootstrap")
         if proj.bootstrap_idx and on_device:
@@ -309,7 +313,11 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
             q_dev = torch.from_numpy(quartets.view(np.int32))
             if hasattr(resolver, "device"):
                 q_dev = q_dev.to(resolver.device)
+        t_prep = time.perf_counter()
         out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
+        if hasattr(resolver, "device"):
+            torch.cuda.synchronize(resolver.device)
+        t_gpu = time.perf_counter()
         idx = proj.bootstrap_idx
         rng_state = RNGStateModel.from_rng(rng)          # generator state after this replicate's draws
         if pending is not None:
@@ -323,7 +331,9 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
             pending = pool.submit(_sink_replicate, proj, *job) if pool is not None else _sink_replicate(proj, *job)
             if pool is None:
                 pending = None
-        logger.info(f"finished rep {idx}")
+        logger.info(f"finished rep {idx}: {len(quartets)} quartets, prepare {t_prep - t_start:.3f} s, resolve "
+                    f"{t_gpu - t_prep:.3f} s ({len(quartets) / max(t_gpu - t_prep, 1e-9):.3g} quartets/s), "
+                    f"hand-off to sink {time.perf_counter() - t_gpu:.3f} s")
         proj.bootstrap_idx += 1
         proj.bootstrap_rng = rng_state
     if pending is not None:
