@@ -63,7 +63,6 @@ struct tq_ctx {
     void *d_planes = nullptr;  size_t cap_planes = 0;
     void *d_quart = nullptr;   size_t cap_quart = 0;
     void *d_out = nullptr;     size_t cap_out = 0;
-    void *h_pin = nullptr;     size_t cap_pin = 0;
     int64_t last_h2d = 0, last_d2h = 0;
 };
 
@@ -73,7 +72,7 @@ int tq_version(void) { return TQ_VERSION; }
 
 const char *tq_last_error(void) { return g_err; }
 
-int64_t tq_launch_count(void) { return tq::g_launches; }
+int64_t tq_launch_count(void) { return tq::g_launches.load(); }
 
 // ------------------------------------------------------------------------------------------
 // plan
@@ -333,7 +332,6 @@ void tq_ctx_destroy(tq_ctx *c)
     DeviceGuard guard(c->device);
     if (c->plan) tq_plan_destroy(c->plan);
     cudaFree(c->d_tmparr); cudaFree(c->d_planes); cudaFree(c->d_quart); cudaFree(c->d_out);
-    if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -382,6 +380,7 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
     const bool same = c->plan && c->key_arr == h_tmparr && c->key_loc == h_locus && c->key_ntips == ntips &&
                       c->key_ncols == ncols && c->key_epoch == epoch && epoch != 0;
     if (!same) {
+        c->key_arr = c->key_loc = nullptr;          // nothing is cached until the rebuild below has succeeded
         if (c->plan) { tq_plan_destroy(c->plan); c->plan = nullptr; }
         if ((rc = tq_plan_create(h_locus, ncols, locus_stride, c->device, c->stream, &c->plan)) != TQ_OK) return rc;
         c->last_h2d += (int64_t)((2 * c->plan->ntiles + 1 + 3 * c->plan->ntiles * tq::kTileLoci) * 4);

@@ -25,7 +25,7 @@
 
 namespace tq {
 
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef TQ_TMEM

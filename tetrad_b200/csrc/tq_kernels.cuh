@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace tq {
 
 constexpr int kTileLoci  = 1024;  // loci per tile = 32 lanes x 32 bits
@@ -37,6 +39,6 @@ cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint
 
 cudaError_t run_microbench(int kind, double *result);
 
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;      // kernels launched by this library since load
 
 }  // namespace tq
