@@ -41,6 +41,9 @@ static constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef TQ_DEFAULT_WS
 #define TQ_DEFAULT_WS 1                       // 1: large launches use the warp-specialised kernel (env TQ_KERNEL=ws|fused overrides)
 #endif
+#ifndef TQ_DEFAULT_MMA
+#define TQ_DEFAULT_MMA 1                      // 1: large launches use the tensor-core count kernel (env TQ_KERNEL=mma|ws|fused overrides)
+#endif
 #ifndef TQ_MIN_CTAS
 #define TQ_MIN_CTAS (TQ_TMEM ? 5 : 4)         // resident CTAs per SM the register budget is sized for
 #endif
@@ -1189,6 +1192,328 @@ resolve_ws_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * kTmemCols) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// Stage 2 on the integer tensor cores.
+//
+//   T[ab][cd] = sum over the tile's 1024 loci of  X_ab[l] * Y_cd[l],   X_ab = A_a & B_b,  Y_cd = C_c & D_d
+//
+// is a 16 x 16 x 1024 product of 0/1 matrices whose rows ARE the merged bit planes.  sm_100a has no
+// native 1-bit MMA (ptxas expands mma.b1 into IMMA + ~100 unpack instructions), but the legacy u8
+// instruction mma.sync.m16n8k32 (SASS IMMA.16832.U8.U8) is native, and a bit plane becomes an u8
+// operand with ONE LOP3 per four loci: word & (0x01010101 << v) holds the bytes {0, 2^v}.  Both
+// operands use the same mask, so all products of one instruction are {0, 4^v}; v = 0..3 on the word
+// and on the word >> 4 cover the eight bits of every byte, and each v has its own s32 accumulator
+// fragment: count = sum_v acc_v >> 2v.  The K order of an MMA is free as long as A and B agree, so lane
+// (g = lane / 4, j = lane % 4) simply feeds bytes j of ITS OWN word pair -- the data is never
+// transposed: the lane reads planes A_p, A_p+2, B_r (rows g and g + 8 of the A operand, p = g / 4,
+// r = g % 4) and C_p, C_p+2, D_r (column g of the two B operands) of words 8 j .. 8 j + 7 from a
+// per-warp shared-memory copy of the tile's 16 merged planes (row stride 34 words: conflict-free
+// 8-byte reads).  Per tile and warp: 16 STS + 24 LDS.64 + ~320 LOP3/SHF + 64 IMMA, against
+// 256 LOP3 + 256 POPC + 128 IADD + the TMEM round trips of the POPC path; nothing runs on the XU pipe,
+// the MMA sums over the whole tile (no cross-lane butterfly), and the counters are 32 registers
+// (measured stand-alone: profiles/probes/imma_count_probe.cu, ~1000 clocks per tile and scheduler
+// against >= 2048 for 256 POPCs).
+// ------------------------------------------------------------------------------------------
+static constexpr int kPStride = 34;                 // words per plane row of the per-warp tile copy
+static constexpr uint32_t kMmaFlushEvery = 16384;   // tiles between accumulator flushes: 16384 * 1024 * 4^3 < 2^31
+
+__device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// acc[v][h][i]: scale 4^v, column half h (cd = 8h ..), fragment register i
+__device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                               const uint32_t (&MC)[4], const uint32_t (&MD)[4],
+                                               uint32_t *P, int lane, int (&acc)[4][2][4])
+{
+    __syncwarp();                                    // the previous tile's reads are over
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        P[(0 + k) * kPStride + lane] = MA[k];
+        P[(4 + k) * kPStride + lane] = MB[k];
+        P[(8 + k) * kPStride + lane] = MC[k];
+        P[(12 + k) * kPStride + lane] = MD[k];
+    }
+    __syncwarp();
+    const int g = lane >> 2, j = lane & 3;
+    const uint32_t *pa = P + (g >> 2) * kPStride + 8 * j;          // A_p; A_p+2 two rows on, C_p eight rows on
+    const uint32_t *pb = P + (4 + (g & 3)) * kPStride + 8 * j;     // B_r; D_r eight rows on
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint2 a0 = *reinterpret_cast<const uint2 *>(pa + 2 * i);
+        const uint2 a1 = *reinterpret_cast<const uint2 *>(pa + 2 * kPStride + 2 * i);
+        const uint2 b = *reinterpret_cast<const uint2 *>(pb + 2 * i);
+        const uint2 c0 = *reinterpret_cast<const uint2 *>(pa + 8 * kPStride + 2 * i);
+        const uint2 c1 = *reinterpret_cast<const uint2 *>(pa + 10 * kPStride + 2 * i);
+        const uint2 d = *reinterpret_cast<const uint2 *>(pb + 8 * kPStride + 2 * i);
+        uint32_t x[2][4], y[2][4];    // x: rows g / g+8 of word W, then of word W';  y: column g of half 0 (W, W'), of half 1 (W, W')
+        x[0][0] = a0.x & b.x; x[0][1] = a1.x & b.x; x[0][2] = a0.y & b.y; x[0][3] = a1.y & b.y;
+        y[0][0] = c0.x & d.x; y[0][1] = c0.y & d.y; y[0][2] = c1.x & d.x; y[0][3] = c1.y & d.y;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { x[1][q] = x[0][q] >> 4; y[1][q] = y[0][q] >> 4; }
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const uint32_t msk = 0x01010101u << v;
+                const uint32_t f0 = x[s][0] & msk, f1 = x[s][1] & msk, f2 = x[s][2] & msk, f3 = x[s][3] & msk;
+                imma_u8(acc[v][0], f0, f1, f2, f3, y[s][0] & msk, y[s][1] & msk);
+                imma_u8(acc[v][1], f0, f1, f2, f3, y[s][2] & msk, y[s][3] & msk);
+            }
+    }
+}
+
+// Add the accumulated counts into T and clear the accumulators.  Lane (g, j) holds rows g and g + 8,
+// columns 2j and 2j + 1 of each column half: no cross-lane step.
+__device__ __forceinline__ void flush_mma(int (&acc)[4][2][4], uint32_t *T, int lane)
+{
+    const int g = lane >> 2, j = lane & 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            uint32_t c0 = 0u, c1 = 0u;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                c0 += (uint32_t)acc[v][h][2 * rr] >> (2 * v);
+                c1 += (uint32_t)acc[v][h][2 * rr + 1] >> (2 * v);
+                acc[v][h][2 * rr] = 0; acc[v][h][2 * rr + 1] = 0;
+            }
+            uint2 *t = reinterpret_cast<uint2 *>(T + (g + 8 * rr) * 16 + 8 * h + 2 * j);
+            uint2 cur = *t;
+            cur.x += c0; cur.y += c1;
+            *t = cur;
+        }
+}
+
+// Stage 1 as in count_quartet (cp.async ring, first usable column per locus), stage 2 by count_tile_mma.
+template <bool kSubsample>
+__device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uint4 *__restrict__ planes,
+                                                  uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane)
+{
+    int acc[4][2][4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[v][h][i] = 0;
+    uint32_t pending = 0;
+    const uint32_t nchunks = plan.row_u4 / kTileWords;
+    const uint32_t t0 = tips.x * plan.row_u4, t1 = tips.y * plan.row_u4;    // row starts, uint4 units
+    const uint32_t t2 = tips.z * plan.row_u4, t3 = tips.w * plan.row_u4;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + lane);
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if ((uint32_t)s < nchunks) issue_chunk(ring_s, planes, s * kTileWords + lane, s, t0, t1, t2, t3);
+        cp_async_commit();
+    }
+    uint32_t u = 0;                                   // rank-chunk index along the rows
+    for (int tile = 0; tile < plan.ntiles; ++tile) {
+        const uint32_t K = __ldg(plan.tile_k + tile);
+        uint32_t taken = 0u;
+        uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
+        uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
+        for (uint32_t k = 0; k < K; ++k, ++u) {
+            {   // keep kStages-1 chunks in flight
+                const uint32_t nu = u + kStages - 1;
+                if (nu < nchunks) issue_chunk(ring_s, planes, nu * kTileWords + lane, nu % kStages, t0, t1, t2, t3);
+                cp_async_commit();
+            }
+            cp_async_wait<kStages - 1>();
+            const uint4 *st = ring + (u % kStages) * (4 * 32) + lane;
+            const uint4 a = st[0], b = st[32], c = st[64], d = st[96];
+            if (kSubsample) {
+                const uint32_t valid = (a.x | a.y | a.z | a.w) & (b.x | b.y | b.z | b.w) &
+                                       (c.x | c.y | c.z | c.w) & (d.x | d.y | d.z | d.w);
+                const uint32_t same = (a.x & b.x & c.x & d.x) | (a.y & b.y & c.y & d.y) |
+                                      (a.z & b.z & c.z & d.z) | (a.w & b.w & c.w & d.w);
+                const uint32_t sel = valid & ~same & ~taken;
+                taken |= sel;
+                MA[0] |= a.x & sel; MA[1] |= a.y & sel; MA[2] |= a.z & sel; MA[3] |= a.w & sel;
+                MB[0] |= b.x & sel; MB[1] |= b.y & sel; MB[2] |= b.z & sel; MB[3] |= b.w & sel;
+                MC[0] |= c.x & sel; MC[1] |= c.y & sel; MC[2] |= c.z & sel; MC[3] |= c.w & sel;
+                MD[0] |= d.x & sel; MD[1] |= d.y & sel; MD[2] |= d.z & sel; MD[3] |= d.w & sel;
+            } else {
+                // full mode (resolve_quartets.py:92-95): every complete column counts; the four
+                // invariant patterns aaaa are zeroed by the caller
+                const uint32_t A[4] = {a.x, a.y, a.z, a.w}, B[4] = {b.x, b.y, b.z, b.w};
+                const uint32_t C[4] = {c.x, c.y, c.z, c.w}, D[4] = {d.x, d.y, d.z, d.w};
+                count_tile_mma(A, B, C, D, P, lane, acc);
+                if (++pending == kMmaFlushEvery) { flush_mma(acc, T, lane); pending = 0; }
+            }
+        }
+        if (kSubsample) {
+            count_tile_mma(MA, MB, MC, MD, P, lane, acc);
+            if (++pending == kMmaFlushEvery) { flush_mma(acc, T, lane); pending = 0; }
+        }
+    }
+    cp_async_wait<0>();
+    flush_mma(acc, T, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised kernel around the tensor-core count path.  A CTA has NC count warps and NS score
+// warps.  The count path has no XU bottleneck and plenty of independent work per warp, so few
+// count warps keep the SM's integer pipes busy; the FP64 Jacobi is bound by its own dependency chains
+// (a score warp issues about one instruction in ten cycles), so most of the register file goes to score
+// warps.  Hand-off through a CTA-wide ring of NC + NS slots of 256 counts: producers and consumers
+// take tickets (one shared-memory atomic each), slot = ticket % slots, full / empty mbarrier per
+// slot, so ANY score warp takes the next finished quartet -- no fixed count -> score pairing.
+// ------------------------------------------------------------------------------------------
+template <int NC, int NS>
+struct __align__(16) MmaShared {
+    static constexpr int kSlots = NC + NS;
+    uint4 ring[NC][kStages][4][32];
+    uint32_t P[NC][16 * kPStride];
+    uint32_t T[kSlots][256];
+    WsSlotMeta meta[kSlots];
+    SvdScratch svd[NS];
+    unsigned long long full[kSlots], empty[kSlots];
+    uint32_t produce, consume;
+};
+
+template <bool kSubsample, int NC, int NS, int kCtas>
+__global__ void __launch_bounds__((NC + NS) * 32, kCtas)
+resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
+                   const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
+                   double *__restrict__ rscor, uint2 *__restrict__ rstat,
+                   uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
+                   uint32_t *__restrict__ status)
+{
+    using Shared = MmaShared<NC, NS>;
+    constexpr int kSlots = Shared::kSlots;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared &sh = *reinterpret_cast<Shared *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSlots; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+        sh.produce = 0u; sh.consume = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t ncount = (int64_t)gridDim.x * NC;                     // count warps in the grid
+    auto quartets_of = [&](int c) -> int64_t {                           // how many quartets count warp c of this CTA resolves
+        const int64_t first = (int64_t)blockIdx.x * NC + c;
+        return first < m ? (m - first + ncount - 1) / ncount : 0;
+    };
+
+    if (warp < NC) {
+        // ------------------------------ count warps ------------------------------
+        const int c = warp;
+        const int64_t n = quartets_of(c);
+        int64_t q = (int64_t)blockIdx.x * NC + c;
+        for (int64_t it = 0; it < n; ++it, q += ncount) {
+            uint32_t ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&sh.produce, 1u);
+            ticket = __shfl_sync(kFull, ticket, 0);
+            const uint32_t slot = ticket % kSlots, use = ticket / kSlots;
+            mbar_wait(&sh.empty[slot], (use & 1u) ^ 1u);                  // slot free (passes at once on its first use)
+            uint32_t *T = sh.T[slot];
+            const uint4 t = __ldg(quartets + q);
+            const bool bad = t.x >= ntips || t.y >= ntips || t.z >= ntips || t.w >= ntips;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
+            __syncwarp();
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane);
+            if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.full[slot]);
+        }
+    } else {
+        // ------------------------------ score warps ------------------------------
+        SvdScratch &sv = sh.svd[warp - NC];
+        int64_t total = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) total += quartets_of(c);
+        while (true) {
+            uint32_t ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&sh.consume, 1u);
+            ticket = __shfl_sync(kFull, ticket, 0);
+            if ((int64_t)ticket >= total) break;
+            const uint32_t slot = ticket % kSlots, use = ticket / kSlots;
+            mbar_wait(&sh.full[slot], use & 1u);
+            uint32_t *T = sh.T[slot];
+            const long long mq = sh.meta[slot].q;
+            const uint4 t = sh.meta[slot].tips;
+            if (mq < 0) {                                                  // tip index out of range
+                const long long q = -1 - mq;
+                if (lane == 0) {
+                    rstat[q] = make_uint2(0xFFFFFFFFu, 0u);
+                    rscor[3 * q] = rscor[3 * q + 1] = rscor[3 * q + 2] = 0.0;
+                    if (status) atomicOr(status, 1u);
+                }
+            } else {
+                const long long q = mq;
+                if (!kSubsample && lane < 4) T[85u * lane] = 0u;          // invariant patterns aaaa, :218
+                __syncwarp();
+                uint32_t nsnps = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t v = T[lane + 32 * i];
+                    nsnps += v;
+                    if (counts) counts[q * 256 + lane + 32 * i] = v;
+                }
+                nsnps = __reduce_add_sync(kFull, nsnps);                    // :226
+                double score[3] = {0.001, 0.001, 0.001};                    // :232
+                uint32_t best, minrank = 0;
+                if (nsnps == 0) {
+                    uint64_t h = seed;
+                    h = splitmix64(h ^ t.x); h = splitmix64(h ^ t.y);
+                    h = splitmix64(h ^ t.z); h = splitmix64(h ^ t.w);
+                    best = (uint32_t)(h % 3ull);                            // stands in for :231
+                } else {
+#ifndef TQ_NO_SVD
+                    svd_scores(T, sv, lane, score, &best, &minrank, 0u);
+#else
+                    best = 0;
+#endif
+                }
+                if (lane == 0) {
+                    rscor[3 * q] = score[0]; rscor[3 * q + 1] = score[1]; rscor[3 * q + 2] = score[2];
+                    rstat[q] = make_uint2(best, nsnps);                     // :251, :264
+                    if (minrank_out) minrank_out[q] = minrank;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.empty[slot]);
+        }
+    }
+}
+
+#ifndef TQ_MMA_NC
+#define TQ_MMA_NC 4                            // count warps per CTA of the tensor-core kernel
+#define TQ_MMA_NS 6                            // score warps per CTA
+#define TQ_MMA_CTAS 2                          // resident CTAs per SM
+#endif
+
+template <bool kSubsample>
+static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, uint32_t ntips, const uint4 *quartets,
+                                      int64_t m, uint64_t seed, double *d_rscor, uint2 *rstat, uint32_t *d_counts,
+                                      uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream)
+{
+    constexpr int NC = TQ_MMA_NC, NS = TQ_MMA_NS, kCtas = TQ_MMA_CTAS;
+    auto kern = resolve_mma_kernel<kSubsample, NC, NS, kCtas>;
+    const size_t smem = sizeof(MmaShared<NC, NS>);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int64_t want = (m + NC - 1) / NC;
+    const int64_t cap = (int64_t)num_sms * kCtas;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    kern<<<grid, (NC + NS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank, d_status);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips,
                            const uint32_t *d_quartets, int64_t m, bool subsample, uint64_t seed,
                            double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
@@ -1213,6 +1538,13 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     // iterations the warp-specialised one wins (C2: 7.67 vs 7.31 M quartets/s); on tiny launches
     // (C1: 495 quartets) its count -> score hand-off is pure latency.  TQ_KERNEL=ws|fused overrides.
     static const char *force = getenv("TQ_KERNEL");
+    const bool use_mma = force ? (strcmp(force, "mma") == 0) : (TQ_DEFAULT_MMA != 0 && m >= (int64_t)num_sms * 64);
+    if (use_mma) {
+        return subsample ? launch_resolve_mma<true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat, d_counts,
+                                                    d_minrank, d_status, num_sms, stream)
+                         : launch_resolve_mma<false>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat, d_counts,
+                                                     d_minrank, d_status, num_sms, stream);
+    }
     const bool use_ws = force ? (strcmp(force, "ws") == 0) : (TQ_DEFAULT_WS != 0 && m >= (int64_t)num_sms * 64);
     if (use_ws && TQ_TMEM) {
         const size_t wsmem = sizeof(WsShared);
