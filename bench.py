@@ -282,18 +282,30 @@ def run_ours(args):
     prof = ROOT / "profiles" / "resolve_traffic.json"
     if prof.exists():
         traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    forced = os.environ.get("TQ_KERNEL")
-    specialised = (forced == "ws") if forced else Q >= sms * 64      # same rule as launch_resolve (tq_kernels.cu)
+    kernel_name = lib.tq_last_kernel().decode()                 # which variant launch_resolve chose (tq_kernels.cu)
+    imma = ctypes.c_double()
+    _lib.check(lib.tq_microbench(local, 4, ctypes.byref(imma)))
+    lop3 = ctypes.c_double()
+    _lib.check(lib.tq_microbench(local, 1, ctypes.byref(lop3)))
+    imma_per_quartet = 64.0 * eng.info["ntiles"]                  # 16 x 16 x 1024 bit-products per tile / (16 x 8 x 32 per IMMA)
+    alu_per_quartet = 32.0 * (320.0 * eng.info["ntiles"] + 36.0 * eng.info["row_words"] / 128.0)   # unpack + stage-1 logic, thread-ops
     roofline = {
-        "bound": "hbm", "kernel": "tq::resolve_ws_kernel<true>" if specialised else "tq::resolve_kernel<true>",
+        "bound": "hbm", "kernel": kernel_name,
         "achieved": achieved, "peak": peak_gbs,
         "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_quartet": algorithmic_bytes_per_quartet(meta["ncols"]),
         "kernel_ms": statistics.mean(kern_ms),
         "popc": {"achieved_popc_per_s": popc_per_quartet * Q / kern_s, "peak_popc_per_s": popc.value,
                  "frac": popc_per_quartet * Q / kern_s / popc.value,
-                 "note": "POPC pipe is the binding unit; peak measured by tq_microbench on this GPU"},
+                 "note": "rate a 256-POPC-per-32-loci implementation would need; the tensor-core count path issues no "
+                         "POPC, so frac > 1 is possible; peak measured by tq_microbench on this GPU"},
+        "imma": {"achieved_per_s": imma_per_quartet * Q / kern_s, "peak_per_s": imma.value,
+                 "frac": imma_per_quartet * Q / kern_s / imma.value,
+                 "note": "warp-level IMMA.16832.U8.U8 (mma.sync m16n8k32 u8) of stage 2; peak measured by tq_microbench kind 4"},
+        "alu": {"achieved_per_s": alu_per_quartet * Q / kern_s, "peak_per_s": 2.0 * lop3.value,
+                "frac": alu_per_quartet * Q / kern_s / (2.0 * lop3.value),
+                "note": "LOP3/SHF thread-ops of the bit-plane unpack (320 per tile and lane) and of stage 1 (36 per rank "
+                        "chunk and lane), the pipe that binds the count warps; peak measured by tq_microbench kind 1 (LOP3 + SHF pairs, counted as two ops)"},
     }
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample ------------------

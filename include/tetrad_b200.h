@@ -170,12 +170,17 @@ int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, cha
  * Measurement helpers (bench.py): pipe micro-benchmarks on `device`.
  * kind 0: POPC  (result: popc32 thread-instructions per second)
  * kind 1: LOP3  (and/or)      kind 2: DFMA        kind 3: device copy (bytes/s, read+write)
+ * kind 4: IMMA.16832.U8.U8 (mma.sync m16n8k32 u8), result: warp-level instructions per second
  * kind 10..14: POPC rate at 16 warps/SM when mixed with nothing / SHFL / LDS.128 / DFMA / ALU work
  */
 int tq_microbench(int device, int kind, double *result);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t tq_launch_count(void);
+
+/* name of the resolve kernel variant the last tq_resolve / tq_resolve_host launched
+ * ("tq::resolve_mma_kernel<true>", ...); a static string, never NULL */
+const char *tq_last_kernel(void);
 
 #ifdef __cplusplus
 }

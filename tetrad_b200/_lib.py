@@ -75,6 +75,8 @@ def _declare(lib):
     lib.tq_last_error.argtypes = []
     lib.tq_launch_count.restype = i64
     lib.tq_launch_count.argtypes = []
+    lib.tq_last_kernel.restype = c.c_char_p
+    lib.tq_last_kernel.argtypes = []
     lib.tq_plan_create.restype = i32
     lib.tq_plan_create.argtypes = [vp, i64, i64, i32, vp, c.POINTER(vp)]
     lib.tq_plan_destroy.restype = None
@@ -112,7 +114,7 @@ def _declare(lib):
 
 
 EXPORTS = [
-    "tq_version", "tq_last_error", "tq_launch_count", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
+    "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
     "tq_plan_destroy",
     "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
     "tq_ctx_last_traffic", "tq_microbench", "tq_format_tsv", "tq_round_scores", "tq_format_qmc",

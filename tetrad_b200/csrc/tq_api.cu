@@ -73,6 +73,7 @@ int tq_version(void) { return TQ_VERSION; }
 const char *tq_last_error(void) { return g_err; }
 
 int64_t tq_launch_count(void) { return tq::g_launches.load(); }
+const char *tq_last_kernel(void) { return tq::g_last_kernel.load(); }
 
 // ------------------------------------------------------------------------------------------
 // plan
@@ -430,7 +431,7 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
 
 int tq_microbench(int device, int kind, double *result)
 {
-    if (!result || kind < 0 || (kind > 3 && (kind < 10 || kind > 14))) return fail(TQ_EINVAL, "tq_microbench: bad arguments");
+    if (!result || kind < 0 || (kind > 4 && (kind < 10 || kind > 14))) return fail(TQ_EINVAL, "tq_microbench: bad arguments");
     DeviceGuard guard(device);
     TQ_CUDA(tq::run_microbench(kind, result));
     return TQ_OK;

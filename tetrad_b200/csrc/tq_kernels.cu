@@ -26,6 +26,7 @@
 namespace tq {
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<const char *> g_last_kernel{"none"};
 
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef TQ_TMEM
@@ -43,6 +44,15 @@ static constexpr unsigned kFull = 0xFFFFFFFFu;
 #endif
 #ifndef TQ_DEFAULT_MMA
 #define TQ_DEFAULT_MMA 1                      // 1: large launches use the tensor-core count kernel (env TQ_KERNEL=mma|ws|fused overrides)
+#endif
+#ifndef TQ_MMA_NC
+#define TQ_MMA_NC 4                           // count warps per CTA of the tensor-core kernel
+#endif
+#ifndef TQ_MMA_NS
+#define TQ_MMA_NS 6                           // score warps per CTA
+#endif
+#ifndef TQ_MMA_CTAS
+#define TQ_MMA_CTAS 2                         // resident CTAs per SM
 #endif
 #ifndef TQ_MIN_CTAS
 #define TQ_MIN_CTAS (TQ_TMEM ? 5 : 4)         // resident CTAs per SM the register budget is sized for
@@ -1214,6 +1224,20 @@ resolve_ws_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips
 // (measured stand-alone: profiles/probes/imma_count_probe.cu, ~1000 clocks per tile and scheduler
 // against >= 2048 for 256 POPCs).
 // ------------------------------------------------------------------------------------------
+#ifdef TQ_MMA_TIMERS                                  // profiling only: clock64 phase accumulators of the tensor-core kernel
+__device__ unsigned long long g_mma_clk[8];         // count: slot wait, stage 2, total, warps; score: full wait, svd, total, warps
+#define TQM_DECL(x) long long x = 0
+#define TQM_T(x) const long long x = clock64()
+#define TQM_ADD(acc, t0) acc += clock64() - (t0)
+#else
+#define TQM_DECL(x)
+#define TQM_T(x)
+#define TQM_ADD(acc, t0)
+#endif
+#ifndef TQ_MMA_STAGES
+#define TQ_MMA_STAGES 5                       // cp.async ring depth of the tensor-core kernel's count warps
+#endif
+static constexpr int kMStages = TQ_MMA_STAGES;
 static constexpr int kPStride = 34;                 // words per plane row of the per-warp tile copy
 static constexpr uint32_t kMmaFlushEvery = 16384;   // tiles between accumulator flushes: 16384 * 1024 * 4^3 < 2^31
 
@@ -1291,7 +1315,11 @@ __device__ __forceinline__ void flush_mma(int (&acc)[4][2][4], uint32_t *T, int 
 // Stage 1 as in count_quartet (cp.async ring, first usable column per locus), stage 2 by count_tile_mma.
 template <bool kSubsample>
 __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uint4 *__restrict__ planes,
-                                                  uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane)
+                                                  uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane
+#ifdef TQ_MMA_TIMERS
+                                                  , long long &clk_stage2
+#endif
+                                                  )
 {
     int acc[4][2][4];
 #pragma unroll
@@ -1306,25 +1334,40 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
     const uint32_t t2 = tips.z * plan.row_u4, t3 = tips.w * plan.row_u4;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + lane);
 #pragma unroll
-    for (int s = 0; s < kStages - 1; ++s) {
+    for (int s = 0; s < kMStages - 1; ++s) {
+#ifndef TQ_DBG_NO_LOAD
         if ((uint32_t)s < nchunks) issue_chunk(ring_s, planes, s * kTileWords + lane, s, t0, t1, t2, t3);
         cp_async_commit();
+#endif
     }
     uint32_t u = 0;                                   // rank-chunk index along the rows
-    for (int tile = 0; tile < plan.ntiles; ++tile) {
+    uint32_t rs = 0, ws = kMStages - 1;               // ring stage read next / written next
+#ifdef TQ_COUNT_TILES                                 // profiling only: count the first tiles, to see the score warps' ceiling
+    const int ntiles = plan.ntiles < TQ_COUNT_TILES ? plan.ntiles : TQ_COUNT_TILES;
+#else
+    const int ntiles = plan.ntiles;
+#endif
+    for (int tile = 0; tile < ntiles; ++tile) {
         const uint32_t K = __ldg(plan.tile_k + tile);
         uint32_t taken = 0u;
         uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
         uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
         for (uint32_t k = 0; k < K; ++k, ++u) {
-            {   // keep kStages-1 chunks in flight
-                const uint32_t nu = u + kStages - 1;
-                if (nu < nchunks) issue_chunk(ring_s, planes, nu * kTileWords + lane, nu % kStages, t0, t1, t2, t3);
+#ifndef TQ_DBG_NO_LOAD
+            {   // keep kMStages-1 chunks in flight
+                const uint32_t nu = u + kMStages - 1;
+                if (nu < nchunks) issue_chunk(ring_s, planes, nu * kTileWords + lane, ws, t0, t1, t2, t3);
                 cp_async_commit();
+                ws = (ws + 1 == kMStages) ? 0u : ws + 1;
             }
-            cp_async_wait<kStages - 1>();
-            const uint4 *st = ring + (u % kStages) * (4 * 32) + lane;
+            cp_async_wait<kMStages - 1>();
+#endif
+            const uint4 *st = ring + rs * (4 * 32) + lane;
+            rs = (rs + 1 == kMStages) ? 0u : rs + 1;
             const uint4 a = st[0], b = st[32], c = st[64], d = st[96];
+#ifdef TQ_DBG_NO_S1
+            if (kSubsample) { MA[0] |= a.x; MB[0] |= b.y; MC[0] |= c.z; MD[0] |= d.w; } else
+#endif
             if (kSubsample) {
                 const uint32_t valid = (a.x | a.y | a.z | a.w) & (b.x | b.y | b.z | b.w) &
                                        (c.x | c.y | c.z | c.w) & (d.x | d.y | d.z | d.w);
@@ -1346,7 +1389,13 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
             }
         }
         if (kSubsample) {
+            TQM_T(ts2);
+#ifndef TQ_DBG_NO_S2
             count_tile_mma(MA, MB, MC, MD, P, lane, acc);
+#else
+            acc[0][0][0] += MA[0] ^ MA[1] ^ MA[2] ^ MA[3] ^ MB[0] ^ MB[1] ^ MB[2] ^ MB[3] ^ MC[0] ^ MC[1] ^ MC[2] ^ MC[3] ^ MD[0] ^ MD[1] ^ MD[2] ^ MD[3];
+#endif
+            TQM_ADD(clk_stage2, ts2);
             if (++pending == kMmaFlushEvery) { flush_mma(acc, T, lane); pending = 0; }
         }
     }
@@ -1366,7 +1415,7 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
 template <int NC, int NS>
 struct __align__(16) MmaShared {
     static constexpr int kSlots = NC + NS;
-    uint4 ring[NC][kStages][4][32];
+    uint4 ring[NC][kMStages][4][32];
     uint32_t P[NC][16 * kPStride];
     uint32_t T[kSlots][256];
     WsSlotMeta meta[kSlots];
@@ -1408,36 +1457,53 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
         const int c = warp;
         const int64_t n = quartets_of(c);
         int64_t q = (int64_t)blockIdx.x * NC + c;
+        TQM_DECL(clk_wait); TQM_DECL(clk_s2); TQM_T(t_begin);
         for (int64_t it = 0; it < n; ++it, q += ncount) {
             uint32_t ticket = 0;
             if (lane == 0) ticket = atomicAdd(&sh.produce, 1u);
             ticket = __shfl_sync(kFull, ticket, 0);
             const uint32_t slot = ticket % kSlots, use = ticket / kSlots;
+            TQM_T(tw);
             mbar_wait(&sh.empty[slot], (use & 1u) ^ 1u);                  // slot free (passes at once on its first use)
+            TQM_ADD(clk_wait, tw);
             uint32_t *T = sh.T[slot];
             const uint4 t = __ldg(quartets + q);
             const bool bad = t.x >= ntips || t.y >= ntips || t.z >= ntips || t.w >= ntips;
 #pragma unroll
             for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
             __syncwarp();
+#ifdef TQ_MMA_TIMERS
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, clk_s2);
+#else
             if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane);
+#endif
             if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.full[slot]);
         }
+#ifdef TQ_MMA_TIMERS
+        if (lane == 0) {
+            atomicAdd(&g_mma_clk[0], (unsigned long long)clk_wait); atomicAdd(&g_mma_clk[1], (unsigned long long)clk_s2);
+            atomicAdd(&g_mma_clk[2], (unsigned long long)(clock64() - t_begin)); atomicAdd(&g_mma_clk[3], 1ull);
+        }
+#endif
     } else {
         // ------------------------------ score warps ------------------------------
         SvdScratch &sv = sh.svd[warp - NC];
         int64_t total = 0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) total += quartets_of(c);
+        TQM_DECL(clk_wait); TQM_DECL(clk_svd); TQM_T(t_begin);
         while (true) {
             uint32_t ticket = 0;
             if (lane == 0) ticket = atomicAdd(&sh.consume, 1u);
             ticket = __shfl_sync(kFull, ticket, 0);
             if ((int64_t)ticket >= total) break;
             const uint32_t slot = ticket % kSlots, use = ticket / kSlots;
+            TQM_T(tw);
             mbar_wait(&sh.full[slot], use & 1u);
+            TQM_ADD(clk_wait, tw);
+            TQM_T(tsv);
             uint32_t *T = sh.T[slot];
             const long long mq = sh.meta[slot].q;
             const uint4 t = sh.meta[slot].tips;
@@ -1481,16 +1547,17 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
                 }
             }
             __syncwarp();
+            TQM_ADD(clk_svd, tsv);
             if (lane == 0) mbar_arrive(&sh.empty[slot]);
         }
+#ifdef TQ_MMA_TIMERS
+        if (lane == 0) {
+            atomicAdd(&g_mma_clk[4], (unsigned long long)clk_wait); atomicAdd(&g_mma_clk[5], (unsigned long long)clk_svd);
+            atomicAdd(&g_mma_clk[6], (unsigned long long)(clock64() - t_begin)); atomicAdd(&g_mma_clk[7], 1ull);
+        }
+#endif
     }
 }
-
-#ifndef TQ_MMA_NC
-#define TQ_MMA_NC 4                            // count warps per CTA of the tensor-core kernel
-#define TQ_MMA_NS 6                            // score warps per CTA
-#define TQ_MMA_CTAS 2                          // resident CTAs per SM
-#endif
 
 template <bool kSubsample>
 static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, uint32_t ntips, const uint4 *quartets,
@@ -1511,6 +1578,22 @@ static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, 
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     kern<<<grid, (NC + NS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank, d_status);
     ++g_launches;
+    g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
+#ifdef TQ_MMA_TIMERS
+    {
+        cudaDeviceSynchronize();
+        unsigned long long h[8];
+        cudaMemcpyFromSymbol(h, g_mma_clk, sizeof(h));
+        const double cw = (double)h[3], sw = (double)h[7], qn = (double)m;
+        fprintf(stderr, "[mma clk] %d+%d warps x %d CTAs/SM, %.0f count warps, %.0f score warps, %.1f quartets per count warp\n"
+                        "  count warp, per quartet: slot wait %.0f, stage 2 %.0f, rest (stage 1 + flush) %.0f, total %.0f\n"
+                        "  score warp, per quartet: wait for counts %.0f, score %.0f; per warp total %.0f of which waiting %.0f\n",
+                NC, NS, kCtas, cw, sw, qn / cw, h[0] / qn, h[1] / qn, (h[2] - h[0] - h[1]) / qn, h[2] / qn,
+                h[4] / qn, h[5] / qn, h[6] / sw, h[4] / sw);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_mma_clk, z, sizeof(z));
+    }
+#endif
     return cudaGetLastError();
 }
 
@@ -1564,8 +1647,10 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
             resolve_ws_kernel<false><<<wgrid, kWsWarps * 32, wsmem, stream>>>(plan, planes, (uint32_t)ntips, quartets, m, seed,
                                                                              d_rscor, rstat, d_counts, d_minrank, d_status);
         ++g_launches;
+        g_last_kernel = subsample ? "tq::resolve_ws_kernel<true>" : "tq::resolve_ws_kernel<false>";
         return cudaGetLastError();
     }
+    g_last_kernel = subsample ? "tq::resolve_kernel<true>" : "tq::resolve_kernel<false>";
     const size_t smem = sizeof(WarpScratch) * kWarps;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1677,6 +1762,29 @@ __global__ void __launch_bounds__(256) copy_kernel(const uint4 *__restrict__ src
         dst[i] = src[i];
 }
 
+// kind 4: issue rate of the legacy u8 tensor-core instruction (IMMA.16832.U8.U8), 6 independent accumulator
+// fragments per warp, operands one bit per byte as in count_tile_mma
+__global__ void __launch_bounds__(512) imma_rate_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = (threadIdx.x * 2654435761u + seed * (i + 1)) & 0x04040404u;
+    b[0] = (threadIdx.x * 40503u + seed) & 0x04040404u; b[1] = b[0] >> 1;
+    int c[6][4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[k][i] = 0;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) imma_u8(c[k], a[0], a[1], a[2], a[3], b[0], b[1]);
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s += (uint32_t)(c[k][0] + c[k][1] + c[k][2] + c[k][3]);
+    if (s == 0x12345u) out[0] = s;
+}
+
 cudaError_t run_microbench(int kind, double *result)
 {
     cudaError_t err;
@@ -1710,6 +1818,22 @@ cudaError_t run_microbench(int kind, double *result)
         }
         cudaFree(out);
         work = (double)blocks * threads * (double)iters * 8.0;
+    } else if (kind == 4) {
+        uint32_t *out = nullptr;
+        if ((err = cudaMalloc(&out, 64)) != cudaSuccess) return err;
+        const int iters = 8192, blocks = sms, threads = 512;
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(e0);
+            imma_rate_kernel<<<blocks, threads>>>(out, iters, rep);
+            ++g_launches;
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best_ms) best_ms = ms;
+        }
+        cudaFree(out);
+        work = (double)blocks * (threads / 32) * (double)iters * 6.0;   // warp-level IMMA instructions
     } else if (kind == 3) {
         const size_t bytes = (size_t)1 << 30;
         uint4 *a = nullptr, *b = nullptr;

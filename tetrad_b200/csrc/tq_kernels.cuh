@@ -40,5 +40,6 @@ cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint
 cudaError_t run_microbench(int kind, double *result);
 
 extern std::atomic<int64_t> g_launches;      // kernels launched by this library since load
+extern std::atomic<const char *> g_last_kernel;   // name of the resolve kernel variant launched last
 
 }  // namespace tq
