@@ -182,6 +182,14 @@ int64_t tq_launch_count(void);
  * ("tq::resolve_mma_kernel<true>", ...); a static string, never NULL */
 const char *tq_last_kernel(void);
 
+/* Tuning / test hooks; process-wide, initialised from the environment (TQ_KERNEL, TQ_MMA_FLUSH).
+ *   "kernel"           0 = chosen by launch size (default), 1 = fused one-warp-per-quartet POPC kernel,
+ *                      2 = warp-specialised POPC kernel, 3 = tensor-core (IMMA) count kernel
+ *   "mma_flush_every"  > 0: tile products between accumulator flushes of the tensor-core kernel
+ *                      (default 16384; tests lower it to reach the flush path), 0 = default
+ * Returns TQ_EINVAL for an unknown name or an out-of-range value. */
+int tq_set_option(const char *name, int64_t value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,9 +18,26 @@ def tb():
     return tetrad_b200
 
 
+@pytest.fixture(params=["fused", "ws", "mma"])
+def kernel(request, tb):
+    """Every resolve-kernel variant behind launch_resolve (tq_kernels.cu): the fused one-warp-per-quartet POPC
+    kernel, the warp-specialised POPC kernel and the tensor-core (IMMA) count kernel.  The default rule picks by
+    launch size, so small test launches would otherwise only ever see the fused kernel."""
+    from tetrad_b200 import _lib
+    _lib.set_kernel(request.param)
+    yield request.param
+    _lib.set_kernel("auto")
+    _lib.check(_lib.load().tq_set_option(b"mma_flush_every", 0))
+
+
+def last_kernel():
+    from tetrad_b200 import _lib
+    return _lib.load().tq_last_kernel().decode()
+
+
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 @pytest.mark.parametrize("mode", ["sub", "full"])
-def test_golden_host_entry(tb, case, mode):
+def test_golden_host_entry(tb, kernel, case, mode):
     """new_infer_resolved_quartets (tq_resolve_host) == reference outputs."""
     g = load_golden(case)
     sub = mode == "sub"
@@ -53,7 +70,7 @@ def test_golden_device_engine(tb, case):
     eng.close()
 
 
-def test_zero_snp_quartets(tb, oracle):
+def test_zero_snp_quartets(tb, oracle, kernel):
     g = load_golden("missing7")
     for seed in (0, 5):
         _, rstat, rscor = tb.new_infer_resolved_quartets(g["tmparr"], g["tmpmap"], g["quartets"], True, seed=seed)
@@ -65,7 +82,7 @@ def test_zero_snp_quartets(tb, oracle):
 
 @pytest.mark.parametrize("shape", [(9, 300, 1100), (16, 2500, 9000), (6, 2, 5), (5, 40, 40)])
 @pytest.mark.parametrize("sub", [True, False])
-def test_seeded_vs_oracle(tb, oracle, shape, sub):
+def test_seeded_vs_oracle(tb, oracle, kernel, shape, sub):
     from itertools import combinations
     from tetrad_b200 import synth
     n, nloci, nsnps = shape
@@ -82,6 +99,7 @@ def test_seeded_vs_oracle(tb, oracle, shape, sub):
     assert_best_matches(rstat[:, 0], oscor, ostat)
     has = ostat[:, 1] > 0
     assert (extra["minrank"][has] == det["minrank"][has]).all()
+    assert {"fused": "resolve_kernel", "ws": "resolve_ws_kernel", "mma": "resolve_mma_kernel"}[kernel] in last_kernel()
 
 
 def test_bootstrap_replicate_vs_oracle(tb, oracle):
@@ -97,7 +115,7 @@ def test_bootstrap_replicate_vs_oracle(tb, oracle):
     assert_scores_close(rscor, oscor, ostat[:, 1])
 
 
-def test_edge_cases(tb):
+def test_edge_cases(tb, kernel):
     g = load_golden("tiny8")
     # empty quartet list
     q, rstat, rscor = tb.new_infer_resolved_quartets(g["tmparr"], g["tmpmap"], np.zeros((0, 4), np.uint32), True)
@@ -123,7 +141,7 @@ def test_edge_cases(tb):
         eng.check_status()
 
 
-def test_many_tiles_and_long_loci(tb, oracle):
+def test_many_tiles_and_long_loci(tb, oracle, kernel):
     """> 1 tile (1024 loci each), one very long locus, loci of length 1."""
     rng = np.random.default_rng(4)
     lens = np.concatenate([[70], rng.integers(1, 7, size=2600), np.ones(300, dtype=np.int64)])
@@ -263,10 +281,12 @@ def test_device_unranking_matches_itertools_and_reference_vectors(tb):
 
 
 @pytest.mark.parametrize("sub", [True, False])
-def test_more_than_63_tiles_exercises_the_counter_flush(tb, oracle, sub):
-    """> 64 512 loci = more than 63 tiles of 1024: the packed 16-bit counters are flushed inside the
-    tile loop (as at the C3-C5 shapes).  Exact counts against the oracle."""
-    from tetrad_b200 import synth
+def test_more_than_63_tiles_exercises_the_counter_flush(tb, oracle, kernel, sub):
+    """> 64 512 loci = more than 63 tiles of 1024: the packed 16-bit counters of the POPC kernels are flushed
+    inside the tile loop (as at the C3-C5 shapes); the tensor-core kernel's scaled s32 accumulators are flushed
+    every 16 384 tile products, lowered here to 5 so that the path runs.  Exact counts against the oracle."""
+    from tetrad_b200 import _lib, synth
+    _lib.check(_lib.load().tq_set_option(b"mma_flush_every", 5))
     d = synth.generate(6, 70_000, 150_000, seed=17)
     db = synth.prepare_database(d.snps, d.snpsmap, seed=17)
     quartets = np.array([[0, 1, 2, 3], [0, 2, 4, 5], [1, 3, 4, 5], [0, 1, 4, 5], [2, 3, 4, 5]], dtype=np.uint32)

@@ -77,6 +77,8 @@ def _declare(lib):
     lib.tq_launch_count.argtypes = []
     lib.tq_last_kernel.restype = c.c_char_p
     lib.tq_last_kernel.argtypes = []
+    lib.tq_set_option.restype = i32
+    lib.tq_set_option.argtypes = [c.c_char_p, i64]
     lib.tq_plan_create.restype = i32
     lib.tq_plan_create.argtypes = [vp, i64, i64, i32, vp, c.POINTER(vp)]
     lib.tq_plan_destroy.restype = None
@@ -114,7 +116,7 @@ def _declare(lib):
 
 
 EXPORTS = [
-    "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
+    "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_set_option", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
     "tq_plan_destroy",
     "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
     "tq_ctx_last_traffic", "tq_microbench", "tq_format_tsv", "tq_round_scores", "tq_format_qmc",
@@ -138,3 +140,11 @@ def load():
 def check(code: int) -> None:
     if code != TQ_OK:
         raise TetradB200Error(code, load().tq_last_error().decode("utf-8", "replace"))
+
+
+KERNELS = {"auto": 0, "fused": 1, "ws": 2, "mma": 3}
+
+
+def set_kernel(name: str) -> None:
+    """Force a resolve-kernel variant ("fused", "ws", "mma") or go back to the size rule ("auto")."""
+    check(load().tq_set_option(b"kernel", KERNELS[name]))

@@ -75,6 +75,22 @@ const char *tq_last_error(void) { return g_err; }
 int64_t tq_launch_count(void) { return tq::g_launches.load(); }
 const char *tq_last_kernel(void) { return tq::g_last_kernel.load(); }
 
+int tq_set_option(const char *name, int64_t value)
+{
+    if (!name) return fail(TQ_EINVAL, "tq_set_option: null name");
+    if (!strcmp(name, "kernel")) {
+        if (value < 0 || value > 3) return fail(TQ_EINVAL, "tq_set_option: kernel must be 0 (auto), 1 (fused), 2 (ws) or 3 (mma)");
+        tq::g_kernel_choice = (int)value;
+        return TQ_OK;
+    }
+    if (!strcmp(name, "mma_flush_every")) {
+        if (value < 0) return fail(TQ_EINVAL, "tq_set_option: mma_flush_every must be >= 0");
+        tq::g_mma_flush = value;
+        return TQ_OK;
+    }
+    return fail(TQ_EINVAL, "tq_set_option: unknown option");
+}
+
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------

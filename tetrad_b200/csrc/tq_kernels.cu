@@ -27,6 +27,21 @@ namespace tq {
 
 std::atomic<int64_t> g_launches{0};
 std::atomic<const char *> g_last_kernel{"none"};
+// Kernel choice and test hooks (tq_set_option in the C ABI; the environment gives the initial values).
+//   g_kernel_choice: 0 = by launch size, 1 = fused (one warp per quartet, POPC), 2 = warp-specialised POPC, 3 = tensor-core count
+static int initial_kernel_choice()
+{
+    const char *e = getenv("TQ_KERNEL");
+    if (!e) return 0;
+    return !strcmp(e, "fused") ? 1 : !strcmp(e, "ws") ? 2 : !strcmp(e, "mma") ? 3 : 0;
+}
+static int64_t initial_mma_flush()
+{
+    const char *e = getenv("TQ_MMA_FLUSH");
+    return e ? atol(e) : 0;
+}
+std::atomic<int> g_kernel_choice{initial_kernel_choice()};
+std::atomic<int64_t> g_mma_flush{initial_mma_flush()};
 
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef TQ_TMEM
@@ -643,7 +658,10 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
 }
 
 static constexpr double kTau2 = 1e-18;    // rotate when gamma^2 > tau^2 * |x|^2 |y|^2  (tau = 1e-9)
-static constexpr double kStop2 = 1e-8;    // a sweep whose largest relative gamma was < 1e-4 is the last
+#ifndef TQ_STOP2
+#define TQ_STOP2 1e-8
+#endif
+static constexpr double kStop2 = TQ_STOP2;    // a sweep whose largest relative gamma was < 1e-4 is the last
 
 __device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], double &nP, double &nQ,
                                               double tiny, bool &big, bool force = false)
@@ -1063,18 +1081,20 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n}\n"
                  ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
-// Wait for the phase with the given parity to complete.  A wait that lasts seconds means a protocol
-// bug: trap (launch error) rather than hang the GPU.
+// Wait for the phase with the given parity to complete.  try_wait suspends the warp in hardware for up to
+// the hinted time (it resumes as soon as the phase completes), so a waiting warp costs a few instructions per
+// millisecond instead of a spin loop that competes for issue slots with the warps it is waiting for
+// (profiles/r01_v6_resolve_ncu.md).  A wait that lasts seconds means a protocol bug: trap (launch error)
+// rather than hang the GPU.
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
     const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
     uint32_t ok = 0;
-    const long long t0 = clock64();
-    while (true) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    for (uint32_t tries = 0;; ++tries) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
         if (ok) break;
-        if (clock64() - t0 > 20000000000ll) __trap();
+        if (tries > (1u << 24)) __trap();
     }
 }
 
@@ -1235,11 +1255,12 @@ __device__ unsigned long long g_mma_clk[8];         // count: slot wait, stage 2
 #define TQM_ADD(acc, t0)
 #endif
 #ifndef TQ_MMA_STAGES
-#define TQ_MMA_STAGES 5                       // cp.async ring depth of the tensor-core kernel's count warps
+#define TQ_MMA_STAGES 4                       // cp.async ring depth of the tensor-core kernel's count warps
 #endif
 static constexpr int kMStages = TQ_MMA_STAGES;
 static constexpr int kPStride = 34;                 // words per plane row of the per-warp tile copy
-static constexpr uint32_t kMmaFlushEvery = 16384;   // tiles between accumulator flushes: 16384 * 1024 * 4^3 < 2^31
+static constexpr uint32_t kMmaFlushEvery = 16384;   // tile products between accumulator flushes: 16384 * 1024 * 4^3 < 2^31
+                                                    // (env TQ_MMA_FLUSH lowers it so that tests reach the flush path)
 
 __device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
@@ -1248,22 +1269,35 @@ __device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a1, u
 }
 
 // acc[v][h][i]: scale 4^v, column half h (cd = 8h ..), fragment register i
+struct MmaLanePtrs {              // per-lane views of the warp's tile copy P, set up once per quartet
+    uint32_t *st;                 // P + lane: where this lane stores its word of every plane
+    const uint32_t *pa;           // A_p words 8j..: A_p+2 two rows on, C_p eight rows on, C_p+2 ten rows on
+    const uint32_t *pb;           // B_r words 8j..: D_r eight rows on
+};
+__device__ __forceinline__ MmaLanePtrs mma_lane_ptrs(uint32_t *P, int lane)
+{
+    const int g = lane >> 2, j = lane & 3;
+    MmaLanePtrs lp;
+    lp.st = P + lane;
+    lp.pa = P + (g >> 2) * kPStride + 8 * j;
+    lp.pb = P + (4 + (g & 3)) * kPStride + 8 * j;
+    return lp;
+}
+
 __device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
                                                const uint32_t (&MC)[4], const uint32_t (&MD)[4],
-                                               uint32_t *P, int lane, int (&acc)[4][2][4])
+                                               const MmaLanePtrs &lp, int (&acc)[4][2][4])
 {
     __syncwarp();                                    // the previous tile's reads are over
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        P[(0 + k) * kPStride + lane] = MA[k];
-        P[(4 + k) * kPStride + lane] = MB[k];
-        P[(8 + k) * kPStride + lane] = MC[k];
-        P[(12 + k) * kPStride + lane] = MD[k];
+        lp.st[(0 + k) * kPStride] = MA[k];
+        lp.st[(4 + k) * kPStride] = MB[k];
+        lp.st[(8 + k) * kPStride] = MC[k];
+        lp.st[(12 + k) * kPStride] = MD[k];
     }
     __syncwarp();
-    const int g = lane >> 2, j = lane & 3;
-    const uint32_t *pa = P + (g >> 2) * kPStride + 8 * j;          // A_p; A_p+2 two rows on, C_p eight rows on
-    const uint32_t *pb = P + (4 + (g & 3)) * kPStride + 8 * j;     // B_r; D_r eight rows on
+    const uint32_t *pa = lp.pa, *pb = lp.pb;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint2 a0 = *reinterpret_cast<const uint2 *>(pa + 2 * i);
@@ -1313,14 +1347,20 @@ __device__ __forceinline__ void flush_mma(int (&acc)[4][2][4], uint32_t *T, int 
 }
 
 // Stage 1 as in count_quartet (cp.async ring, first usable column per locus), stage 2 by count_tile_mma.
+// Differences that matter at two count warps per scheduler (profiles/r01_v6_resolve_ncu.md): the tile's rank
+// count is fetched one tile ahead (it was a global-load latency on the critical path of every tile), the
+// ring reads are issued before the next chunk's address arithmetic and cp.async so that their latency is
+// covered, and the global addresses are four 64-bit row pointers plus one running 32-bit offset.
 template <bool kSubsample>
 __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uint4 *__restrict__ planes,
-                                                  uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane
+                                                  uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane,
+                                                  uint32_t flush_every
 #ifdef TQ_MMA_TIMERS
                                                   , long long &clk_stage2
 #endif
                                                   )
 {
+    static_assert((kMStages & (kMStages - 1)) == 0, "ring depth must be a power of two");
     int acc[4][2][4];
 #pragma unroll
     for (int v = 0; v < 4; ++v)
@@ -1328,43 +1368,52 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[v][h][i] = 0;
+    const MmaLanePtrs lp = mma_lane_ptrs(P, lane);
     uint32_t pending = 0;
     const uint32_t nchunks = plan.row_u4 / kTileWords;
-    const uint32_t t0 = tips.x * plan.row_u4, t1 = tips.y * plan.row_u4;    // row starts, uint4 units
-    const uint32_t t2 = tips.z * plan.row_u4, t3 = tips.w * plan.row_u4;
+    const uint4 *g0 = planes + (size_t)tips.x * plan.row_u4 + lane, *g1 = planes + (size_t)tips.y * plan.row_u4 + lane;
+    const uint4 *g2 = planes + (size_t)tips.z * plan.row_u4 + lane, *g3 = planes + (size_t)tips.w * plan.row_u4 + lane;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + lane);
+    auto issue = [&](uint32_t chunk, uint32_t stage) {
+        const uint32_t s = ring_s + stage * (4 * 32 * 16), off = chunk * kTileWords;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g0 + off) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 512), "l"(g1 + off) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1024), "l"(g2 + off) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1536), "l"(g3 + off) : "memory");
+    };
+#ifndef TQ_DBG_NO_LOAD
 #pragma unroll
     for (int s = 0; s < kMStages - 1; ++s) {
-#ifndef TQ_DBG_NO_LOAD
-        if ((uint32_t)s < nchunks) issue_chunk(ring_s, planes, s * kTileWords + lane, s, t0, t1, t2, t3);
+        if ((uint32_t)s < nchunks) issue(s, s);
         cp_async_commit();
-#endif
     }
+#endif
     uint32_t u = 0;                                   // rank-chunk index along the rows
-    uint32_t rs = 0, ws = kMStages - 1;               // ring stage read next / written next
 #ifdef TQ_COUNT_TILES                                 // profiling only: count the first tiles, to see the score warps' ceiling
     const int ntiles = plan.ntiles < TQ_COUNT_TILES ? plan.ntiles : TQ_COUNT_TILES;
 #else
     const int ntiles = plan.ntiles;
 #endif
+    uint32_t Knext = ntiles > 0 ? __ldg(plan.tile_k) : 0u;
     for (int tile = 0; tile < ntiles; ++tile) {
-        const uint32_t K = __ldg(plan.tile_k + tile);
+        const uint32_t K = Knext;
+        if (tile + 1 < ntiles) Knext = __ldg(plan.tile_k + tile + 1);
         uint32_t taken = 0u;
         uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
         uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
         for (uint32_t k = 0; k < K; ++k, ++u) {
 #ifndef TQ_DBG_NO_LOAD
-            {   // keep kMStages-1 chunks in flight
-                const uint32_t nu = u + kMStages - 1;
-                if (nu < nchunks) issue_chunk(ring_s, planes, nu * kTileWords + lane, ws, t0, t1, t2, t3);
-                cp_async_commit();
-                ws = (ws + 1 == kMStages) ? 0u : ws + 1;
-            }
-            cp_async_wait<kMStages - 1>();
+            cp_async_wait<kMStages - 2>();            // chunk u has landed (chunks u+1 .. u+kMStages-2 may be in flight)
 #endif
-            const uint4 *st = ring + rs * (4 * 32) + lane;
-            rs = (rs + 1 == kMStages) ? 0u : rs + 1;
+            const uint4 *st = ring + (u & (kMStages - 1)) * (4 * 32) + lane;
             const uint4 a = st[0], b = st[32], c = st[64], d = st[96];
+#ifndef TQ_DBG_NO_LOAD
+            {   // refill the stage read in the previous iteration; keeps kMStages-1 chunks in flight
+                const uint32_t nu = u + kMStages - 1;
+                if (nu < nchunks) issue(nu, nu & (kMStages - 1));
+                cp_async_commit();
+            }
+#endif
 #ifdef TQ_DBG_NO_S1
             if (kSubsample) { MA[0] |= a.x; MB[0] |= b.y; MC[0] |= c.z; MD[0] |= d.w; } else
 #endif
@@ -1384,19 +1433,19 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
                 // invariant patterns aaaa are zeroed by the caller
                 const uint32_t A[4] = {a.x, a.y, a.z, a.w}, B[4] = {b.x, b.y, b.z, b.w};
                 const uint32_t C[4] = {c.x, c.y, c.z, c.w}, D[4] = {d.x, d.y, d.z, d.w};
-                count_tile_mma(A, B, C, D, P, lane, acc);
-                if (++pending == kMmaFlushEvery) { flush_mma(acc, T, lane); pending = 0; }
+                count_tile_mma(A, B, C, D, lp, acc);
+                if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
             }
         }
         if (kSubsample) {
             TQM_T(ts2);
 #ifndef TQ_DBG_NO_S2
-            count_tile_mma(MA, MB, MC, MD, P, lane, acc);
+            count_tile_mma(MA, MB, MC, MD, lp, acc);
 #else
             acc[0][0][0] += MA[0] ^ MA[1] ^ MA[2] ^ MA[3] ^ MB[0] ^ MB[1] ^ MB[2] ^ MB[3] ^ MC[0] ^ MC[1] ^ MC[2] ^ MC[3] ^ MD[0] ^ MD[1] ^ MD[2] ^ MD[3];
 #endif
             TQM_ADD(clk_stage2, ts2);
-            if (++pending == kMmaFlushEvery) { flush_mma(acc, T, lane); pending = 0; }
+            if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
         }
     }
     cp_async_wait<0>();
@@ -1430,7 +1479,7 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
                    const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
                    double *__restrict__ rscor, uint2 *__restrict__ rstat,
                    uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
-                   uint32_t *__restrict__ status)
+                   uint32_t *__restrict__ status, uint32_t flush_every)
 {
     using Shared = MmaShared<NC, NS>;
     constexpr int kSlots = Shared::kSlots;
@@ -1473,9 +1522,9 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
             for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
             __syncwarp();
 #ifdef TQ_MMA_TIMERS
-            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, clk_s2);
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every, clk_s2);
 #else
-            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane);
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every);
 #endif
             if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
             __syncwarp();
@@ -1576,7 +1625,10 @@ static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, 
     const int64_t want = (m + NC - 1) / NC;
     const int64_t cap = (int64_t)num_sms * kCtas;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    kern<<<grid, (NC + NS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank, d_status);
+    const int64_t fv = g_mma_flush.load();
+    const uint32_t flush_every = (fv >= 1 && fv < (int64_t)kMmaFlushEvery) ? (uint32_t)fv : kMmaFlushEvery;
+    kern<<<grid, (NC + NS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank, d_status,
+                                                 flush_every);
     ++g_launches;
     g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
 #ifdef TQ_MMA_TIMERS
@@ -1620,15 +1672,15 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     // Two variants of the same fused kernel.  With enough quartets to keep every warp busy for many
     // iterations the warp-specialised one wins (C2: 7.67 vs 7.31 M quartets/s); on tiny launches
     // (C1: 495 quartets) its count -> score hand-off is pure latency.  TQ_KERNEL=ws|fused overrides.
-    static const char *force = getenv("TQ_KERNEL");
-    const bool use_mma = force ? (strcmp(force, "mma") == 0) : (TQ_DEFAULT_MMA != 0 && m >= (int64_t)num_sms * 64);
+    const int force = g_kernel_choice.load();
+    const bool use_mma = force ? (force == 3) : (TQ_DEFAULT_MMA != 0 && m >= (int64_t)num_sms * 64);
     if (use_mma) {
         return subsample ? launch_resolve_mma<true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat, d_counts,
                                                     d_minrank, d_status, num_sms, stream)
                          : launch_resolve_mma<false>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat, d_counts,
                                                      d_minrank, d_status, num_sms, stream);
     }
-    const bool use_ws = force ? (strcmp(force, "ws") == 0) : (TQ_DEFAULT_WS != 0 && m >= (int64_t)num_sms * 64);
+    const bool use_ws = force ? (force == 2) : (TQ_DEFAULT_WS != 0 && m >= (int64_t)num_sms * 64);
     if (use_ws && TQ_TMEM) {
         const size_t wsmem = sizeof(WsShared);
         static bool ws_attr = false;

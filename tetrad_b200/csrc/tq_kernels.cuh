@@ -40,6 +40,8 @@ cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint
 cudaError_t run_microbench(int kind, double *result);
 
 extern std::atomic<int64_t> g_launches;      // kernels launched by this library since load
+extern std::atomic<int> g_kernel_choice;          // 0 by launch size, 1 fused, 2 warp-specialised POPC, 3 tensor-core count
+extern std::atomic<int64_t> g_mma_flush;          // > 0: tile products between accumulator flushes of the tensor-core kernel (tests)
 extern std::atomic<const char *> g_last_kernel;   // name of the resolve kernel variant launched last
 
 }  // namespace tq
