@@ -60,14 +60,16 @@ static constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef TQ_DEFAULT_MMA
 #define TQ_DEFAULT_MMA 1                      // 1: large launches use the tensor-core count kernel (env TQ_KERNEL=mma|ws|fused overrides)
 #endif
+// Warp mix of the tensor-core kernel.  Measured at C2 (M quartets/s): 8+11 x1 CTA 9.83, 8+12 x1 9.63, 10+10 x1 9.56,
+// 4+6 x2 9.32-9.52, 5+5 x2 9.24, 9+11 x1 8.95, 7+13 x1 8.91, 3+7 x2 8.02 (profiles/r01_v6_resolve_ncu.md).
 #ifndef TQ_MMA_NC
-#define TQ_MMA_NC 4                           // count warps per CTA of the tensor-core kernel
+#define TQ_MMA_NC 8                           // count warps per CTA of the tensor-core kernel
 #endif
 #ifndef TQ_MMA_NS
-#define TQ_MMA_NS 6                           // score warps per CTA
+#define TQ_MMA_NS 11                          // score warps per CTA
 #endif
 #ifndef TQ_MMA_CTAS
-#define TQ_MMA_CTAS 2                         // resident CTAs per SM
+#define TQ_MMA_CTAS 1                         // resident CTAs per SM
 #endif
 #ifndef TQ_MIN_CTAS
 #define TQ_MIN_CTAS (TQ_TMEM ? 5 : 4)         // resident CTAs per SM the register budget is sized for
