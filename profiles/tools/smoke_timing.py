@@ -1,5 +1,5 @@
 import sys, time, ctypes
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+from pathlib import Path; R = str(Path(__file__).resolve().parent.parent.parent); sys.path.insert(0, R); sys.path.insert(0, R + "/tests")
 import numpy as np, torch
 import tetrad_b200
 from tetrad_b200 import _lib, synth

@@ -1,8 +1,8 @@
 """Per-call wall time of the host entry new_infer_resolved_quartets (tq_resolve_host) at a BASELINE shape.
-usage: python profiles/time_e2e.py [C2|C3]"""
+usage: python profiles/tools/time_e2e.py [C2|C3]"""
 import sys, time
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 import numpy as np, torch
 import tetrad_b200
 from tetrad_b200 import synth

@@ -1,8 +1,8 @@
 """Time one resolve launch of a BASELINE shape on the device (CUDA events, best of 3 after a warm-up).
-usage: [TQ_LIB=path/to/variant.so] [TQ_KERNEL=mma|ws|fused] python profiles/time_resolve.py [C2|C3] [sub|full|both]"""
+usage: [TQ_LIB=path/to/variant.so] [TQ_KERNEL=mma|ws|fused] python profiles/tools/time_resolve.py [C2|C3] [sub|full|both]"""
 import os, sys
 from pathlib import Path
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import numpy as np, torch
 from tetrad_b200 import _lib
