@@ -1092,11 +1092,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 {
     const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
     uint32_t ok = 0;
+    long long t0 = 0;
     for (uint32_t tries = 0;; ++tries) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000000u) : "memory");
         if (ok) break;
-        if (tries > (1u << 24)) __trap();
+        if ((tries & 1023u) == 1023u) {                                 // ~10 s at 2 GHz: a protocol bug, not a wait
+            const long long now = clock64();
+            if (t0 == 0) t0 = now; else if (now - t0 > 20000000000ll) __trap();
+        }
     }
 }
 
@@ -1256,6 +1260,10 @@ __device__ unsigned long long g_mma_clk[8];         // count: slot wait, stage 2
 #define TQM_T(x)
 #define TQM_ADD(acc, t0)
 #endif
+#ifndef TQ_MMA_TMA
+#define TQ_MMA_TMA 0                          // 1: count warps fill their ring with TMA bulk copies (cp.async.bulk + mbarrier); measured
+                                              // slower than cp.async at this depth (7.76 vs 9.81 M quartets/s at C2), kept for reference
+#endif
 #ifndef TQ_MMA_STAGES
 #define TQ_MMA_STAGES 4                       // cp.async ring depth of the tensor-core kernel's count warps
 #endif
@@ -1355,8 +1363,8 @@ __device__ __forceinline__ void flush_mma(int (&acc)[4][2][4], uint32_t *T, int 
 // covered, and the global addresses are four 64-bit row pointers plus one running 32-bit offset.
 template <bool kSubsample>
 __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uint4 *__restrict__ planes,
-                                                  uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane,
-                                                  uint32_t flush_every
+                                                  uint4 tips, const uint4 *ring, unsigned long long *ring_full, uint32_t &ring_pos,
+                                                  uint32_t *P, uint32_t *T, int lane, uint32_t flush_every
 #ifdef TQ_MMA_TIMERS
                                                   , long long &clk_stage2
 #endif
@@ -1373,11 +1381,37 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
     const MmaLanePtrs lp = mma_lane_ptrs(P, lane);
     uint32_t pending = 0;
     const uint32_t nchunks = plan.row_u4 / kTileWords;
+#if TQ_MMA_TMA
+    // TMA bulk copies: lanes 0..3 each own one tip row and copy its 512-byte rank chunk with one cp.async.bulk that
+    // completes on the stage's mbarrier; lane 0 arms the barrier with the stage's 2 KB.  The other 28 lanes issue
+    // nothing and compute no addresses.  `ring_pos` runs on across quartets (stage = pos % depth, parity = pos / depth).
+    const uint32_t my_tip = (lane & 3) == 0 ? tips.x : (lane & 3) == 1 ? tips.y : (lane & 3) == 2 ? tips.z : tips.w;
+    const uint4 *grow = planes + (size_t)my_tip * plan.row_u4;
+    const uint32_t ring_row_s = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)(lane & 3) * 512u;
+    const uint32_t full_s = (uint32_t)__cvta_generic_to_shared(ring_full);
+    const uint32_t pos0 = ring_pos;
+    auto issue = [&](uint32_t chunk) {
+        const uint32_t stage = (pos0 + chunk) & (kMStages - 1);
+        const uint32_t bar = full_s + stage * 8u;
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(2048u) : "memory");
+        if (lane < 4)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(ring_row_s + stage * 2048u), "l"(grow + (size_t)chunk * kTileWords), "r"(512u), "r"(bar) : "memory");
+    };
+#ifndef TQ_DBG_NO_LOAD
+    __syncwarp();                                     // the previous quartet's ring reads are over
+#pragma unroll
+    for (int s = 0; s < kMStages - 1; ++s)
+        if ((uint32_t)s < nchunks) issue(s);
+#endif
+    ring_pos = pos0 + nchunks;
+#else
     const uint4 *g0 = planes + (size_t)tips.x * plan.row_u4 + lane, *g1 = planes + (size_t)tips.y * plan.row_u4 + lane;
     const uint4 *g2 = planes + (size_t)tips.z * plan.row_u4 + lane, *g3 = planes + (size_t)tips.w * plan.row_u4 + lane;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + lane);
-    auto issue = [&](uint32_t chunk, uint32_t stage) {
-        const uint32_t s = ring_s + stage * (4 * 32 * 16), off = chunk * kTileWords;
+    const uint32_t pos0 = 0;
+    auto issue = [&](uint32_t chunk) {
+        const uint32_t s = ring_s + (chunk & (kMStages - 1)) * (4 * 32 * 16), off = chunk * kTileWords;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g0 + off) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 512), "l"(g1 + off) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1024), "l"(g2 + off) : "memory");
@@ -1386,9 +1420,10 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
 #ifndef TQ_DBG_NO_LOAD
 #pragma unroll
     for (int s = 0; s < kMStages - 1; ++s) {
-        if ((uint32_t)s < nchunks) issue(s, s);
+        if ((uint32_t)s < nchunks) issue(s);
         cp_async_commit();
     }
+#endif
 #endif
     uint32_t u = 0;                                   // rank-chunk index along the rows
 #ifdef TQ_COUNT_TILES                                 // profiling only: count the first tiles, to see the score warps' ceiling
@@ -1405,15 +1440,24 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
         uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
         for (uint32_t k = 0; k < K; ++k, ++u) {
 #ifndef TQ_DBG_NO_LOAD
+#if TQ_MMA_TMA
+            mbar_wait(ring_full + ((pos0 + u) & (kMStages - 1)), ((pos0 + u) / kMStages) & 1u);   // chunk u has landed
+#else
             cp_async_wait<kMStages - 2>();            // chunk u has landed (chunks u+1 .. u+kMStages-2 may be in flight)
 #endif
-            const uint4 *st = ring + (u & (kMStages - 1)) * (4 * 32) + lane;
+#endif
+            const uint4 *st = ring + ((pos0 + u) & (kMStages - 1)) * (4 * 32) + lane;
             const uint4 a = st[0], b = st[32], c = st[64], d = st[96];
 #ifndef TQ_DBG_NO_LOAD
             {   // refill the stage read in the previous iteration; keeps kMStages-1 chunks in flight
                 const uint32_t nu = u + kMStages - 1;
-                if (nu < nchunks) issue(nu, nu & (kMStages - 1));
+#if TQ_MMA_TMA
+                __syncwarp();                         // every lane's reads of that stage have returned
+                if (nu < nchunks) issue(nu);
+#else
+                if (nu < nchunks) issue(nu);
                 cp_async_commit();
+#endif
             }
 #endif
 #ifdef TQ_DBG_NO_S1
@@ -1450,7 +1494,9 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
             if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
         }
     }
+#if !TQ_MMA_TMA
     cp_async_wait<0>();
+#endif
     flush_mma(acc, T, lane);
 }
 
@@ -1467,6 +1513,7 @@ template <int NC, int NS>
 struct __align__(16) MmaShared {
     static constexpr int kSlots = NC + NS;
     uint4 ring[NC][kMStages][4][32];
+    unsigned long long ring_full[NC][kMStages];     // TMA completion barrier of every ring stage (TQ_MMA_TMA)
     uint32_t P[NC][16 * kPStride];
     uint32_t T[kSlots][256];
     WsSlotMeta meta[kSlots];
@@ -1492,6 +1539,8 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+        for (int c = 0; c < NC; ++c)
+            for (int s = 0; s < kMStages; ++s) mbar_init(&sh.ring_full[c][s], 1);
         sh.produce = 0u; sh.consume = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -1509,6 +1558,7 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
         const int64_t n = quartets_of(c);
         int64_t q = (int64_t)blockIdx.x * NC + c;
         TQM_DECL(clk_wait); TQM_DECL(clk_s2); TQM_T(t_begin);
+        uint32_t ring_pos = 0;
         for (int64_t it = 0; it < n; ++it, q += ncount) {
             uint32_t ticket = 0;
             if (lane == 0) ticket = atomicAdd(&sh.produce, 1u);
@@ -1524,9 +1574,9 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
             for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
             __syncwarp();
 #ifdef TQ_MMA_TIMERS
-            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every, clk_s2);
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.ring_full[c], ring_pos, sh.P[c], T, lane, flush_every, clk_s2);
 #else
-            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every);
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.ring_full[c], ring_pos, sh.P[c], T, lane, flush_every);
 #endif
             if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
             __syncwarp();
