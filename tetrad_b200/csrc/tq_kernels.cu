@@ -60,13 +60,14 @@ static constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef TQ_DEFAULT_MMA
 #define TQ_DEFAULT_MMA 1                      // 1: large launches use the tensor-core count kernel (env TQ_KERNEL=mma|ws|fused overrides)
 #endif
-// Warp mix of the tensor-core kernel.  Measured at C2 (M quartets/s): 8+11 x1 CTA 9.83, 8+12 x1 9.63, 10+10 x1 9.56,
-// 4+6 x2 9.32-9.52, 5+5 x2 9.24, 9+11 x1 8.95, 7+13 x1 8.91, 3+7 x2 8.02 (profiles/r01_v6_resolve_ncu.md).
+// Warp mix of the tensor-core kernel, one CTA per SM.  Measured at C2 (M quartets/s) with score warps that take four
+// quartets at a time: 8+8 10.88, 7+9 10.42, 8+7 10.18, 7+8 10.05, 9+7 9.70, 10+6 9.67, 10+7 9.50, 6+9 9.28, 9+8 9.22
+// (three-matrix score warps before that: 8+11 9.83, 4+6 x2 CTAs 9.32-9.52; profiles/r01_v6_resolve_ncu.md).
 #ifndef TQ_MMA_NC
 #define TQ_MMA_NC 8                           // count warps per CTA of the tensor-core kernel
 #endif
 #ifndef TQ_MMA_NS
-#define TQ_MMA_NS 11                          // score warps per CTA
+#define TQ_MMA_NS 8                           // score warps per CTA
 #endif
 #ifndef TQ_MMA_CTAS
 #define TQ_MMA_CTAS 1                         // resident CTAs per SM
@@ -933,6 +934,239 @@ __device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int l
 }
 
 // ------------------------------------------------------------------------------------------
+// Scores of up to FOUR quartets at a time (tensor-core kernel).  svd_scores above keeps lanes 24-31 idle: three
+// matrices of 8 lanes each.  Here the 12 flattenings of four quartets go through the same QR + Jacobi code in three
+// passes of four matrices, all 32 lanes busy: a quarter fewer passes per quartet.  Pass r, lane group m = lane / 8
+// works on matrix 4r + m = flattening (4r + m) % 3 of quartet (4r + m) / 3; the sorted singular values of the 12
+// matrices are parked in shared memory and lanes 0..3 finish one quartet each (rank, minrank, tail norms, argmin).
+// ------------------------------------------------------------------------------------------
+struct __align__(16) SvdScratch4 {
+    double M[4][16][kLdm];                      // flattenings M[m][col][row]; later W (R factors) / exchange buffer
+    double piv[4][16];                          // pivot-column buffer during the QR; unsorted singular values
+    double sig[12][16];                         // sorted singular values of the 12 matrices
+};
+
+// Tbase: the CTA's slot array (256 counts per slot); slots: slot index of quartet j in byte j; actmask bit j: quartet j
+// is present and has SNPs.  Lane j < 4 receives the result of quartet j.
+__device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, uint32_t actmask, SvdScratch4 &sv, int lane,
+                                         double (&score_out)[3], uint32_t &best_out, uint32_t &minrank_out)
+{
+    const int m = lane >> 3, s = lane & 7;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int mi = 4 * pass + m, qi = mi / 3, f = mi - 3 * qi;
+        const bool act = (actmask >> qi) & 1u;
+        if (!__any_sync(kFull, act)) continue;      // none of this pass's four matrices exists (fewer than four quartets)
+        const uint32_t *T = Tbase + ((slots >> (8 * qi)) & 0xFFu) * 256u;
+        __syncwarp();
+        // this group's flattening (resolve_quartets.py:63,67-72), stored column-major; 32 of its 256 entries per lane
+        double fro2 = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int p = s + 8 * i;
+            const int a = p >> 6, b = (p >> 4) & 3, c = (p >> 2) & 3, d = p & 3;
+            const double v = act ? (double)T[p] : 0.0;
+            const int col = (f == 0) ? 4 * c + d : (f == 1) ? 4 * b + d : 4 * b + c;
+            const int row = (f == 0) ? 4 * a + b : (f == 1) ? 4 * a + c : 4 * a + d;
+            sv.M[m][col][row] = v;
+            fro2 = fma(v, v, fro2);
+        }
+        fro2 += __shfl_xor_sync(kFull, fro2, 4);
+        fro2 += __shfl_xor_sync(kFull, fro2, 2);
+        fro2 += __shfl_xor_sync(kFull, fro2, 1);
+        const double tiny = (kEps * kEps) * fro2;       // columns this small are null directions
+        __syncwarp();
+        double P[16], Q[16];
+        {
+            const double2 *cp = reinterpret_cast<const double2 *>(&sv.M[m][s][0]);
+            const double2 *cq = reinterpret_cast<const double2 *>(&sv.M[m][s + 8][0]);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double2 x = cp[r], y = cq[r];
+                P[2 * r] = x.x; P[2 * r + 1] = x.y; Q[2 * r] = y.x; Q[2 * r + 1] = y.y;
+            }
+        }
+        __syncwarp();                                    // M is free from here on: reuse it below
+
+        // QR preconditioner, as in svd_scores: pivoted modified Gram-Schmidt inside the 8-lane group, then the Jacobi
+        // runs on the rows of R.
+        {
+            double *W = &sv.M[0][0][0];                  // [4][16 rows k][16 cols j], 8 KB
+            bool doneP = !act, doneQ = !act;
+            double mP = 0.0, mQ = 0.0;                   // squared norms of the remaining parts of P, Q
+#pragma unroll 1
+            for (int k = 0; k < 16; ++k) {
+                if ((k & 3) == 0) {                      // exact every 4th step, downdated in between
+                    mP = 0.0; mQ = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) { mP = fma(P[r], P[r], mP); mQ = fma(Q[r], Q[r], mQ); }
+                }
+                const double nP = doneP ? -1.0 : mP, nQ = doneQ ? -1.0 : mQ;
+                double best = (nP >= nQ) ? nP : nQ;
+                int idx = (nP >= nQ) ? s : s + 8;
+#pragma unroll
+                for (int off = 4; off > 0; off >>= 1) {
+                    const double ob = __shfl_xor_sync(kFull, best, off);
+                    const int oi = __shfl_xor_sync(kFull, idx, off);
+                    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+                }
+                const bool any = best >= 0.0;            // a column of this matrix is still unprocessed
+                double2 *pv = reinterpret_cast<double2 *>(&sv.piv[m][0]);
+                if (idx == s) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) pv[r] = make_double2(P[2 * r], P[2 * r + 1]);
+                } else if (idx == s + 8) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) pv[r] = make_double2(Q[2 * r], Q[2 * r + 1]);
+                }
+                __syncwarp();
+                double dP = 0.0, dQ = 0.0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const double2 x = pv[r];
+                    dP = fma(x.x, P[2 * r], dP); dP = fma(x.y, P[2 * r + 1], dP);
+                    dQ = fma(x.x, Q[2 * r], dQ); dQ = fma(x.y, Q[2 * r + 1], dQ);
+                }
+                const double pp = __shfl_sync(kFull, (idx == s) ? dP : dQ, (lane & ~7) | (idx & 7));
+                const bool live = any && pp > tiny;      // else the pivot is a null direction: retire it with a zero row
+                const double safe = live ? pp : 1.0;
+                double rinv;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rinv) : "d"(safe));
+                rinv = rinv * fma(-0.5 * safe, rinv * rinv, 1.5);
+                rinv = rinv * fma(-0.5 * safe, rinv * rinv, 1.5);
+                const double inv = rinv * rinv;
+                const bool useP = live && !doneP, useQ = live && !doneQ;
+                const double rP = useP ? dP * rinv : 0.0, rQ = useQ ? dQ * rinv : 0.0;
+                W[(m * 16 + k) * 16 + s] = rP;
+                W[(m * 16 + k) * 16 + s + 8] = rQ;
+                mP = fmax(fma(-rP, rP, mP), 0.0);
+                mQ = fmax(fma(-rQ, rQ, mQ), 0.0);
+                const double cP = useP ? -dP * inv : 0.0, cQ = useQ ? -dQ * inv : 0.0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const double2 x = pv[r];
+                    P[2 * r] = fma(cP, x.x, P[2 * r]); P[2 * r + 1] = fma(cP, x.y, P[2 * r + 1]);
+                    Q[2 * r] = fma(cQ, x.x, Q[2 * r]); Q[2 * r + 1] = fma(cQ, x.y, Q[2 * r + 1]);
+                }
+                __syncwarp();
+                if (any && idx == s) doneP = true;
+                if (any && idx == s + 8) doneQ = true;
+            }
+            __syncwarp();
+            {                                            // rows s and s+8 of R become this lane's columns
+                const double2 *cp = reinterpret_cast<const double2 *>(W + (m * 16 + s) * 16);
+                const double2 *cq = reinterpret_cast<const double2 *>(W + (m * 16 + s + 8) * 16);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const double2 x = cp[r], y = cq[r];
+                    P[2 * r] = x.x; P[2 * r + 1] = x.y; Q[2 * r] = y.x; Q[2 * r + 1] = y.y;
+                }
+            }
+            __syncwarp();
+        }
+        double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][9 double2] (144 B stride)
+
+        for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+            double nP = 0.0, nQ = 0.0;                   // refresh the cached squared norms
+#pragma unroll
+            for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
+            bool big = false;
+#pragma unroll 1
+            for (int g = 8; g >= 1; g >>= 1) {
+                for (int r = 0; r < g; ++r) {
+                    jacobi_rotate(P, Q, nP, nQ, tiny, big);
+                    if (r + 1 < g) {                     // Q moves one lane down inside its group of g
+                        const int src = (lane & ~(g - 1)) | ((lane + 1) & (g - 1));
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) Q[k] = __shfl_sync(kFull, Q[k], src);
+                        nQ = __shfl_sync(kFull, nQ, src);
+                    }
+                }
+                if (g > 1) {
+                    const int h = g >> 1;
+                    const bool lower = (lane & (g - 1)) < h;
+                    double2 *mine = xbuf + lane * 9;
+                    if (lower) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) mine[k] = make_double2(Q[2 * k], Q[2 * k + 1]);
+                        mine[8] = make_double2(nQ, 0.0);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) mine[k] = make_double2(P[2 * k], P[2 * k + 1]);
+                        mine[8] = make_double2(nP, 0.0);
+                    }
+                    __syncwarp();
+                    const double2 *theirs = xbuf + (lower ? lane + h : lane - h) * 9;
+                    if (lower) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { const double2 x = theirs[k]; Q[2 * k] = x.x; Q[2 * k + 1] = x.y; }
+                        nQ = theirs[8].x;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { const double2 x = theirs[k]; P[2 * k] = x.x; P[2 * k + 1] = x.y; }
+                        nP = theirs[8].x;
+                    }
+                    __syncwarp();
+                }
+            }
+            if (!__any_sync(kFull, big)) break;
+        }
+
+        // singular values = column norms; sort descending per matrix by rank counting
+        {
+            double nP = 0.0, nQ = 0.0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
+            __syncwarp();
+            sv.piv[m][s] = sqrt(nP); sv.piv[m][s + 8] = sqrt(nQ);
+        }
+        __syncwarp();
+        for (int c = lane; c < 64; c += 32) {
+            const int mm = c >> 4, col = c & 15;
+            const double val = sv.piv[mm][col];
+            int pos = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const double u = sv.piv[mm][j];
+                pos += (u > val || (u == val && j < col)) ? 1 : 0;
+            }
+            sv.sig[4 * pass + mm][pos] = val;
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    // lane j < 4 finishes quartet j: rank = #{sigma > sigma_max * 16 * eps} (numpy.linalg.matrix_rank, :243),
+    // minrank (:246), tail norms (:248), first argmin (:251)
+    if (lane < 4 && ((actmask >> lane) & 1u)) {
+        int mr = 16;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const double *sg = sv.sig[3 * lane + f];
+            const double tol = sg[0] * (16.0 * kEps);
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rank += (sg[j] > tol) ? 1 : 0;
+            mr = min(mr, rank);
+        }
+        mr = min(mr, 10);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const double *sg = sv.sig[3 * lane + f];
+            double sc = 0.0;
+            for (int j = mr; j < 16; ++j) sc = fma(sg[j], sg[j], sc);
+            score_out[f] = sqrt(sc);
+        }
+        uint32_t best = 0;
+        double lo = score_out[0];
+        if (score_out[1] < lo) { best = 1; lo = score_out[1]; }
+        if (score_out[2] < lo) { best = 2; }
+        best_out = best;
+        minrank_out = (uint32_t)mr;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
 // fused resolve kernel: one warp per quartet, persistent grid-stride over groups of kWarps
 // consecutive quartets (neighbours in lexicographic order share tips -> L1 hits)
 // ------------------------------------------------------------------------------------------
@@ -1511,13 +1745,13 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
 // ------------------------------------------------------------------------------------------
 template <int NC, int NS>
 struct __align__(16) MmaShared {
-    static constexpr int kSlots = NC + NS;
+    static constexpr int kSlots = NC + 4 * NS;      // every count warp fills one slot, every score warp holds up to four
     uint4 ring[NC][kMStages][4][32];
     unsigned long long ring_full[NC][kMStages];     // TMA completion barrier of every ring stage (TQ_MMA_TMA)
     uint32_t P[NC][16 * kPStride];
     uint32_t T[kSlots][256];
     WsSlotMeta meta[kSlots];
-    SvdScratch svd[NS];
+    SvdScratch4 svd[NS];
     unsigned long long full[kSlots], empty[kSlots];
     uint32_t produce, consume;
 };
@@ -1590,33 +1824,39 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
 #endif
     } else {
         // ------------------------------ score warps ------------------------------
-        SvdScratch &sv = sh.svd[warp - NC];
+        // A score warp takes up to four finished quartets at a time (svd_scores4: 12 matrices in three passes of four).
+        SvdScratch4 &sv = sh.svd[warp - NC];
         int64_t total = 0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) total += quartets_of(c);
         TQM_DECL(clk_wait); TQM_DECL(clk_svd); TQM_T(t_begin);
         while (true) {
-            uint32_t ticket = 0;
-            if (lane == 0) ticket = atomicAdd(&sh.consume, 1u);
-            ticket = __shfl_sync(kFull, ticket, 0);
-            if ((int64_t)ticket >= total) break;
-            const uint32_t slot = ticket % kSlots, use = ticket / kSlots;
+            uint32_t ticket0 = 0;
+            if (lane == 0) ticket0 = atomicAdd(&sh.consume, 4u);
+            ticket0 = __shfl_sync(kFull, ticket0, 0);
+            if ((int64_t)ticket0 >= total) break;
+            const int nq = (int)((total - (int64_t)ticket0) < 4 ? (total - (int64_t)ticket0) : 4);
+            uint32_t slots = 0u, actmask = 0u, my_nsnps = 0u, my_best = 0u;
+            long long my_q = -1;                                           // lane j < 4: quartet j of this batch
             TQM_T(tw);
-            mbar_wait(&sh.full[slot], use & 1u);
-            TQM_ADD(clk_wait, tw);
-            TQM_T(tsv);
-            uint32_t *T = sh.T[slot];
-            const long long mq = sh.meta[slot].q;
-            const uint4 t = sh.meta[slot].tips;
-            if (mq < 0) {                                                  // tip index out of range
-                const long long q = -1 - mq;
-                if (lane == 0) {
-                    rstat[q] = make_uint2(0xFFFFFFFFu, 0u);
-                    rscor[3 * q] = rscor[3 * q + 1] = rscor[3 * q + 2] = 0.0;
-                    if (status) atomicOr(status, 1u);
+#pragma unroll 1
+            for (int j = 0; j < nq; ++j) {
+                const uint32_t ticket = ticket0 + (uint32_t)j;
+                const uint32_t slot = ticket % kSlots, use = ticket / kSlots;
+                mbar_wait(&sh.full[slot], use & 1u);
+                slots |= slot << (8 * j);
+                uint32_t *T = sh.T[slot];
+                const long long mq = sh.meta[slot].q;
+                const uint4 t = sh.meta[slot].tips;
+                if (mq < 0) {                                              // tip index out of range
+                    const long long q = -1 - mq;
+                    if (lane == 0) {
+                        rstat[q] = make_uint2(0xFFFFFFFFu, 0u);
+                        rscor[3 * q] = rscor[3 * q + 1] = rscor[3 * q + 2] = 0.0;
+                        if (status) atomicOr(status, 1u);
+                    }
+                    continue;
                 }
-            } else {
-                const long long q = mq;
                 if (!kSubsample && lane < 4) T[85u * lane] = 0u;          // invariant patterns aaaa, :218
                 __syncwarp();
                 uint32_t nsnps = 0;
@@ -1624,32 +1864,37 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
                 for (int i = 0; i < 8; ++i) {
                     const uint32_t v = T[lane + 32 * i];
                     nsnps += v;
-                    if (counts) counts[q * 256 + lane + 32 * i] = v;
+                    if (counts) counts[mq * 256 + lane + 32 * i] = v;
                 }
                 nsnps = __reduce_add_sync(kFull, nsnps);                    // :226
-                double score[3] = {0.001, 0.001, 0.001};                    // :232
-                uint32_t best, minrank = 0;
+                uint32_t best = 0;
                 if (nsnps == 0) {
                     uint64_t h = seed;
                     h = splitmix64(h ^ t.x); h = splitmix64(h ^ t.y);
                     h = splitmix64(h ^ t.z); h = splitmix64(h ^ t.w);
                     best = (uint32_t)(h % 3ull);                            // stands in for :231
                 } else {
+                    actmask |= 1u << j;
+                }
+                if (lane == j) { my_q = mq; my_nsnps = nsnps; my_best = best; }
+            }
+            TQM_ADD(clk_wait, tw);
+            TQM_T(tsv);
+            static_assert(kSlots <= 256, "slot indices travel in one byte each");
+            double score[3] = {0.001, 0.001, 0.001};                        // :232
+            uint32_t minrank = 0;
 #ifndef TQ_NO_SVD
-                    svd_scores(T, sv, lane, score, &best, &minrank, 0u);
-#else
-                    best = 0;
+            if (actmask) svd_scores4(&sh.T[0][0], slots, actmask, sv, lane, score, my_best, minrank);
 #endif
-                }
-                if (lane == 0) {
-                    rscor[3 * q] = score[0]; rscor[3 * q + 1] = score[1]; rscor[3 * q + 2] = score[2];
-                    rstat[q] = make_uint2(best, nsnps);                     // :251, :264
-                    if (minrank_out) minrank_out[q] = minrank;
-                }
+            if (lane < 4 && my_q >= 0) {
+                rscor[3 * my_q] = score[0]; rscor[3 * my_q + 1] = score[1]; rscor[3 * my_q + 2] = score[2];
+                rstat[my_q] = make_uint2(my_best, my_nsnps);                // :251, :264
+                if (minrank_out) minrank_out[my_q] = minrank;
             }
             __syncwarp();
             TQM_ADD(clk_svd, tsv);
-            if (lane == 0) mbar_arrive(&sh.empty[slot]);
+            if (lane == 0)
+                for (int j = 0; j < nq; ++j) mbar_arrive(&sh.empty[(ticket0 + (uint32_t)j) % kSlots]);
         }
 #ifdef TQ_MMA_TIMERS
         if (lane == 0) {
