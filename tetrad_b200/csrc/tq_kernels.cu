@@ -667,7 +667,7 @@ static constexpr double kTau2 = 1e-18;    // rotate when gamma^2 > tau^2 * |x|^2
 static constexpr double kStop2 = TQ_STOP2;    // a sweep whose largest relative gamma was < 1e-4 is the last
 
 __device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], double &nP, double &nQ,
-                                              double tiny, bool &big, bool force = false)
+                                              double tiny, bool &big, bool force = false, bool enable = true)
 {
     double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
 #pragma unroll
@@ -677,7 +677,7 @@ __device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], 
     }
     const double ga = (g0 + g1) + (g2 + g3);
     const double ab = nP * nQ, gg = ga * ga;
-    if (force || (nP > tiny && nQ > tiny && gg > kTau2 * ab)) {
+    if (force || (enable && nP > tiny && nQ > tiny && gg > kTau2 * ab)) {
         big |= gg > kStop2 * ab;
         // Rotation that zeroes gamma:  with a = |Q|^2 - |P|^2, b = 2 gamma, r = sqrt(a^2 + b^2):
         //   cos^2 = (1 + |a| / r) / 2,   sin = sign(a) * b / (2 r cos),   tan = sin / cos.
@@ -1066,6 +1066,9 @@ __device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, 
         }
         double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][9 double2] (144 B stride)
 
+        // A matrix stops rotating after ITS last sweep, whatever the other three of the pass still need: the result of a
+        // quartet must not depend on which quartets happen to share its batch (run-to-run reproducibility).
+        bool gdone = !act;
         for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
             double nP = 0.0, nQ = 0.0;                   // refresh the cached squared norms
 #pragma unroll
@@ -1074,7 +1077,7 @@ __device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, 
 #pragma unroll 1
             for (int g = 8; g >= 1; g >>= 1) {
                 for (int r = 0; r < g; ++r) {
-                    jacobi_rotate(P, Q, nP, nQ, tiny, big);
+                    jacobi_rotate(P, Q, nP, nQ, tiny, big, false, !gdone);
                     if (r + 1 < g) {                     // Q moves one lane down inside its group of g
                         const int src = (lane & ~(g - 1)) | ((lane + 1) & (g - 1));
 #pragma unroll
@@ -1109,7 +1112,9 @@ __device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, 
                     __syncwarp();
                 }
             }
-            if (!__any_sync(kFull, big)) break;
+            const uint32_t bigs = __ballot_sync(kFull, big);
+            if (((bigs >> (lane & ~7)) & 0xFFu) == 0u) gdone = true;
+            if (__all_sync(kFull, gdone)) break;
         }
 
         // singular values = column norms; sort descending per matrix by rank counting
