@@ -1971,11 +1971,13 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     const uint4 *planes = reinterpret_cast<const uint4 *>(d_planes);
     const uint4 *quartets = reinterpret_cast<const uint4 *>(d_quartets);
     uint2 *rstat = reinterpret_cast<uint2 *>(d_rstat);
-    // Two variants of the same fused kernel.  With enough quartets to keep every warp busy for many
-    // iterations the warp-specialised one wins (C2: 7.67 vs 7.31 M quartets/s); on tiny launches
-    // (C1: 495 quartets) its count -> score hand-off is pure latency.  TQ_KERNEL=ws|fused overrides.
+    // Three variants of the same device code.  On tiny launches (C1: 495 quartets) a count -> score hand-off is pure
+    // latency, so the homogeneous kernel runs; from 16 quartets per SM the tensor-core kernel; the warp-specialised
+    // POPC kernel only when forced.  tq_set_option("kernel", ..) / TQ_KERNEL=mma|ws|fused override.
     const int force = g_kernel_choice.load();
-    const bool use_mma = force ? (force == 3) : (TQ_DEFAULT_MMA != 0 && m >= (int64_t)num_sms * 64);
+    // Size rule (profiles/tools/time_small.py, C2 matrix, M quartets/s fused / ws / mma): 1 184 quartets 4.5 / 3.7 / 4.1,
+    // 2 368: 6.0 / 5.4 / 6.2, 4 736: 7.1 / 6.3 / 8.0, 37 888: 7.4 / 7.6 / 10.7 -- the tensor-core kernel from 16 quartets per SM.
+    const bool use_mma = force ? (force == 3) : (TQ_DEFAULT_MMA != 0 && m >= (int64_t)num_sms * 16);
     if (use_mma) {
         return subsample ? launch_resolve_mma<true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat, d_counts,
                                                     d_minrank, d_status, num_sms, stream)
