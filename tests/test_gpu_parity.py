@@ -318,3 +318,28 @@ def test_c3_shape_random_quartets_sampled_parity(tb, oracle):
     assert (rstat.cpu().numpy().view(np.uint32)[pick] == ostat).all()
     assert_scores_close(rscor.cpu().numpy()[pick], oscor, ostat[:, 1])
     assert (minrank.cpu().numpy()[pick] == det["minrank"]).all()
+
+
+@pytest.mark.parametrize("sub", [True, False])
+def test_kernel_variants_agree_bit_for_bit(tb, sub):
+    """The three resolve kernels differ in how they count (POPC vs tensor cores) and in how many flattenings share a
+    Jacobi pass, but every flattening goes through the same arithmetic and stops after its own last sweep: counts,
+    nsnps, best split and the f64 scores are identical bits, also between two runs of the same kernel."""
+    from tetrad_b200 import _lib, synth
+    d = synth.generate(14, 4000, 15000, seed=5)
+    db = synth.prepare_database(d.snps, d.snpsmap, seed=5)
+    from itertools import combinations
+    quartets = np.array(list(combinations(range(14), 4)), dtype=np.uint32)
+    eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+    outs = []
+    try:
+        for name in ("fused", "ws", "mma", "mma"):
+            _lib.set_kernel(name)
+            rstat, rscor, counts, minrank = eng.resolve(quartets, sub, want_counts=True)
+            outs.append((rstat.cpu().numpy().copy(), rscor.cpu().numpy().copy(), counts.cpu().numpy().copy(),
+                         minrank.cpu().numpy().copy()))
+    finally:
+        _lib.set_kernel("auto")
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert a.tobytes() == b.tobytes()

@@ -837,6 +837,9 @@ __device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int l
     }
     double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][9 double2] (144 B stride)
 
+    // A matrix stops rotating after ITS last sweep, whatever the other two still need: every flattening then goes
+    // through exactly the same arithmetic here and in svd_scores4, and the three kernel variants agree bit for bit.
+    bool gdone = lane >= 24;
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
         double nP = 0.0, nQ = 0.0;                   // refresh the cached squared norms
 #pragma unroll
@@ -845,7 +848,7 @@ __device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int l
 #pragma unroll 1
         for (int g = 8; g >= 1; g >>= 1) {
             for (int r = 0; r < g; ++r) {
-                jacobi_rotate(P, Q, nP, nQ, tiny, big, (debug & 64u) != 0);
+                jacobi_rotate(P, Q, nP, nQ, tiny, big, (debug & 64u) != 0, !gdone);
                 if (r + 1 < g && !(debug & 16u)) {   // Q moves one lane down inside its group of g
                     const int src = (lane & ~(g - 1)) | ((lane + 1) & (g - 1));
 #pragma unroll
@@ -883,7 +886,9 @@ __device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int l
             }
         }
         if (debug & 32u) { if (sweep == 8) break; else continue; }
-        if (!__any_sync(kFull, big)) break;
+        const uint32_t bigs = __ballot_sync(kFull, big);
+        if (((bigs >> (lane & ~7)) & 0xFFu) == 0u) gdone = true;
+        if (__all_sync(kFull, gdone)) break;
     }
 
     // singular values = column norms; sort descending per matrix by rank counting
