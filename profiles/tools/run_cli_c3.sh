@@ -12,6 +12,6 @@ c = synth.CONFIGS["C3"]
 t = time.time(); d = synth.generate(c["ntips"], c["nloci"], c["nsnps"], seed=1234)
 database.write_snps_input(Path("$W/c3.snps.hdf5"), d.snps, d.snpsmap, d.names); print("input written in %.1f s" % (time.time() - t))
 PY
-/usr/bin/time -v python -m tetrad_b200 init $W/c3.snps.hdf5 -n c3 -w $W -q 1000000 -r 42 -s 2>&1 | grep -E "Elapsed|init|loci|error" | head
-/usr/bin/time -v python -m tetrad_b200 run $W/c3.json -b 3 2>&1 | grep -E "Elapsed|replicate|resolve|sink|prepare|quartets/s|error|Error" | head -30
+python -m tetrad_b200 init $W/c3.snps.hdf5 -n c3 -w $W -q 1000000 -r 42 -s 2>&1 | tail -5
+python -m tetrad_b200 run $W/c3.json -b 3 2>&1 | tail -30
 ls -la $W | head -20
