@@ -1915,6 +1915,15 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
     }
 }
 
+// cudaFuncSetAttribute is per device: remember which devices of this process have the attribute (one bit each).
+static bool attribute_needed(std::atomic<uint64_t> &done)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    return (done.fetch_or(bit) & bit) == 0;
+}
+
 template <bool kSubsample>
 static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, uint32_t ntips, const uint4 *quartets,
                                       int64_t m, uint64_t seed, double *d_rscor, uint2 *rstat, uint32_t *d_counts,
@@ -1923,11 +1932,10 @@ static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, 
     constexpr int NC = TQ_MMA_NC, NS = TQ_MMA_NS, kCtas = TQ_MMA_CTAS;
     auto kern = resolve_mma_kernel<kSubsample, NC, NS, kCtas>;
     const size_t smem = sizeof(MmaShared<NC, NS>);
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<uint64_t> attr{0};
+    if (attribute_needed(attr)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
+        if (e != cudaSuccess) { attr = 0; return e; }
     }
     const int64_t want = (m + NC - 1) / NC;
     const int64_t cap = (int64_t)num_sms * kCtas;
@@ -1992,11 +2000,10 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     const bool use_ws = force ? (force == 2) : (TQ_DEFAULT_WS != 0 && m >= (int64_t)num_sms * 64);
     if (use_ws && TQ_TMEM) {
         const size_t wsmem = sizeof(WsShared);
-        static bool ws_attr = false;
-        if (!ws_attr) {
+        static std::atomic<uint64_t> ws_attr{0};
+        if (attribute_needed(ws_attr)) {
             cudaFuncSetAttribute(resolve_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
             cudaFuncSetAttribute(resolve_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
-            ws_attr = true;
         }
         const int64_t wwant = (m + kWsCount - 1) / kWsCount;
         const int64_t wcap = (int64_t)num_sms * 2;
@@ -2013,11 +2020,10 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     }
     g_last_kernel = subsample ? "tq::resolve_kernel<true>" : "tq::resolve_kernel<false>";
     const size_t smem = sizeof(WarpScratch) * kWarps;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_set{0};
+    if (attribute_needed(attr_set)) {
         cudaFuncSetAttribute(resolve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(resolve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
     }
     if (subsample)
         resolve_kernel<true><<<grid, kWarps * 32, smem, stream>>>(plan, planes, (uint32_t)ntips, quartets,
