@@ -1504,6 +1504,10 @@ __device__ unsigned long long g_mma_clk[8];         // count: slot wait, stage 2
 #define TQM_T(x)
 #define TQM_ADD(acc, t0)
 #endif
+#ifndef TQ_MMA_SPLIT
+#define TQ_MMA_SPLIT 0
+#endif
+
 #ifndef TQ_MMA_TMA
 #define TQ_MMA_TMA 0                          // 1: count warps fill their ring with TMA bulk copies (cp.async.bulk + mbarrier); measured
                                               // slower than cp.async at this depth (7.76 vs 9.81 M quartets/s at C2), kept for reference
@@ -1766,8 +1770,11 @@ struct __align__(16) MmaShared {
     uint32_t produce, consume;
 };
 
+template <int NC, int NS>
+constexpr int mma_launch_warps() { return NC + NS; }
+
 template <bool kSubsample, int NC, int NS, int kCtas>
-__global__ void __launch_bounds__((NC + NS) * 32, kCtas)
+__global__ void __launch_bounds__(mma_launch_warps<NC, NS>() * 32, kCtas)
 resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
                    const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
                    double *__restrict__ rscor, uint2 *__restrict__ rstat,
@@ -1796,9 +1803,32 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
         return first < m ? (m - first + ncount - 1) / ncount : 0;
     };
 
-    if (warp < NC) {
+    // Role of a warp.  Warp w runs on scheduler w % 4, and a score warp that shares a scheduler with count warps is starved
+    // by them (score 190 k clocks per quartet against 75 k on a scheduler of its own: the count warps are nearly always
+    // ready to issue).  TQ_MMA_SPLIT 0: warps 0..NC-1 count, the rest score, every scheduler gets both roles.
+    // 1: schedulers 0-1 only count, 2-3 only score (NC == NS, both even).  2: schedulers 0-2 only count (NS warps each),
+    // scheduler 3 only scores (NS warps).  (setmaxnreg works on groups of four consecutive warps, i.e. one warp of every
+    // scheduler, so idle filler warps cannot hand their registers to the others: the mixes are limited to these.)
+#ifdef TQ_MMA_ROLEMASK                               // bit w set: warp w counts (profiling: any placement of NC count warps)
+    static_assert(__builtin_popcount(TQ_MMA_ROLEMASK) == NC, "TQ_MMA_ROLEMASK must have NC bits set");
+    const bool is_count = (TQ_MMA_ROLEMASK >> warp) & 1u;
+    const uint32_t below = (1u << warp) - 1u;
+    const int role_idx = is_count ? __popc(TQ_MMA_ROLEMASK & below) : __popc(~(uint32_t)TQ_MMA_ROLEMASK & below);
+#elif TQ_MMA_SPLIT == 2
+    static_assert(NC == 3 * NS, "TQ_MMA_SPLIT=2: three count warps and one score warp in every group of four warps");
+    const bool is_count = (warp & 3) < 3;
+    const int role_idx = is_count ? (warp >> 2) * 3 + (warp & 3) : (warp >> 2);
+#elif TQ_MMA_SPLIT == 1
+    static_assert(NC == NS && NC % 2 == 0, "TQ_MMA_SPLIT=1 needs as many count as score warps");
+    const bool is_count = (warp & 3) < 2;
+    const int role_idx = (warp >> 2) * 2 + (warp & 1);
+#else
+    const bool is_count = warp < NC;
+    const int role_idx = is_count ? warp : warp - NC;
+#endif
+    if (is_count) {
         // ------------------------------ count warps ------------------------------
-        const int c = warp;
+        const int c = role_idx;
         const int64_t n = quartets_of(c);
         int64_t q = (int64_t)blockIdx.x * NC + c;
         TQM_DECL(clk_wait); TQM_DECL(clk_s2); TQM_T(t_begin);
@@ -1835,7 +1865,7 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
     } else {
         // ------------------------------ score warps ------------------------------
         // A score warp takes up to four finished quartets at a time (svd_scores4: 12 matrices in three passes of four).
-        SvdScratch4 &sv = sh.svd[warp - NC];
+        SvdScratch4 &sv = sh.svd[role_idx];
         int64_t total = 0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) total += quartets_of(c);
@@ -1942,7 +1972,7 @@ static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, 
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     const int64_t fv = g_mma_flush.load();
     const uint32_t flush_every = (fv >= 1 && fv < (int64_t)kMmaFlushEvery) ? (uint32_t)fv : kMmaFlushEvery;
-    kern<<<grid, (NC + NS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank, d_status,
+    kern<<<grid, mma_launch_warps<NC, NS>() * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank, d_status,
                                                  flush_every);
     ++g_launches;
     g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
