@@ -62,6 +62,9 @@ int  tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride,
 /* Same plan from the run lengths alone (run i covers the next h_run_len[i] columns): used for
  * bootstrap replicates, whose instance lengths are known before any column is materialised. */
 int  tq_plan_create_runs(const uint32_t *h_run_len, int64_t nruns, int device, void *stream, tq_plan **out);
+/* The device tables of a plan are stream-ordered memory (cudaMallocAsync) of the stream given at creation:
+ * tq_plan_destroy frees them in that stream's order without synchronising the device, so work already enqueued
+ * on that stream may still use the plan; work on OTHER streams must have completed before the call. */
 void tq_plan_destroy(tq_plan *plan);
 
 /* info[0]=ncols  [1]=nloci  [2]=ntiles  [3]=row_words (u32 words per tip row of the packed matrix)

@@ -45,6 +45,7 @@ struct tq_plan {
     int num_sms = 0;
     int64_t ncols = 0, nloci = 0, ntiles = 0, row_u4 = 0, max_len = 0, padded_cols = 0;
     void *d_tables = nullptr;      // one allocation: tile_off | tile_k | loc_start | loc_len
+    cudaStream_t stream = nullptr; // the tables are stream-ordered memory of the stream the plan was created on
     std::vector<uint32_t> h_tables; // host copy of the same tables
     size_t o_off = 0, o_k = 0, o_start = 0, o_len = 0, o_run = 0;
     tq::PlanDev dev{};
@@ -94,6 +95,20 @@ int tq_set_option(const char *name, int64_t value)
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
+// Let the device's default memory pool keep what is freed into it (its default gives memory back at every
+// synchronisation, which would turn cudaMallocAsync into cudaMalloc again).  Once per device and process.
+static cudaError_t keep_pool_cached(int device)
+{
+    static std::atomic<uint64_t> done{0};
+    const uint64_t bit = 1ull << (device & 63);
+    if (done.fetch_or(bit) & bit) return cudaSuccess;
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = 256ull << 20;          // plan tables are a few MB; cap what the pool may hold on to
+    return cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+}
+
 // Build a plan from locus runs given as (first column, length) in column order.
 static int build_plan(const std::vector<uint32_t> &run_start, const std::vector<uint32_t> &run_len, int64_t ncols,
                       int device, void *stream, tq_plan **out)
@@ -145,13 +160,17 @@ static int build_plan(const std::vector<uint32_t> &run_start, const std::vector<
 
     DeviceGuard guard(device);
     cudaError_t e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_tables, (total + 4) * sizeof(uint32_t));
+    // Stream-ordered allocation from the device's default pool: a replicate loop creates and destroys one plan per
+    // replicate, and cudaMalloc / cudaFree (which synchronises the whole device) were the jitter of the host entry.
+    if (e == cudaSuccess) e = keep_pool_cached(device);
+    p->stream = (cudaStream_t)stream;
+    if (e == cudaSuccess) e = cudaMallocAsync(&p->d_tables, (total + 4) * sizeof(uint32_t), p->stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(p->d_tables, tables.data(), (total + 4) * sizeof(uint32_t),
                             cudaMemcpyHostToDevice, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);   // `tables` is pageable
     if (e != cudaSuccess) {
-        if (p->d_tables) cudaFree(p->d_tables);
+        if (p->d_tables) cudaFreeAsync(p->d_tables, p->stream);
         delete p;
         return fail(TQ_ECUDA, "tq_plan_create: %s", cudaGetErrorString(e));
     }
@@ -237,9 +256,9 @@ int tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k, ui
 void tq_plan_destroy(tq_plan *plan)
 {
     if (!plan) return;
-    if (plan->d_tables) {
+    if (plan->d_tables) {                 // freed in stream order: work already enqueued on the plan's stream still sees the tables
         DeviceGuard guard(plan->device);
-        cudaFree(plan->d_tables);
+        cudaFreeAsync(plan->d_tables, plan->stream);
     }
     delete plan;
 }
