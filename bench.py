@@ -150,7 +150,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 popcount + f64 svd",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 counts + f64 svd (numpy / LAPACK)",
         "data": "synthetic",
         "config": {"workload": f"{args.config}: {meta['ntips']} tips, {meta['nloci']} loci, {meta['ncols']} SNPs, "
                                f"{len(quartets)} quartets, subsample_snps=True, 0 bootstraps",
@@ -321,7 +321,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 popcount + f64 svd", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> s32 tensor-core counts (bit-exact integers) + f64 svd", "data": "synthetic",
         "config": {"workload": f"{args.config}: {meta['ntips']} tips, {meta['nloci']} loci, {meta['ncols']} SNPs, "
                                f"{Q} quartets per replicate, subsample_snps=True, one replicate per GPU per step",
                    "l2": "flushed between steps (256 MiB write outside the per-step CUDA events)",
