@@ -660,7 +660,10 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
     return x ^ (x >> 31);
 }
 
-static constexpr double kTau2 = 1e-18;    // rotate when gamma^2 > tau^2 * |x|^2 |y|^2  (tau = 1e-9)
+#ifndef TQ_TAU2
+#define TQ_TAU2 1e-18
+#endif
+static constexpr double kTau2 = TQ_TAU2;  // rotate when gamma^2 > tau^2 * |x|^2 |y|^2  (tau = 1e-9)
 #ifndef TQ_STOP2
 #define TQ_STOP2 1e-8
 #endif
