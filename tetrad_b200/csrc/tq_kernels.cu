@@ -669,8 +669,22 @@ static constexpr double kTau2 = TQ_TAU2;  // rotate when gamma^2 > tau^2 * |x|^2
 #endif
 static constexpr double kStop2 = TQ_STOP2;    // a sweep whose largest relative gamma was < 1e-4 is the last
 
-__device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], double &nP, double &nQ,
-                                              double tiny, bool &big, bool force = false, bool enable = true)
+// Self-scaling ("fast") rotations: a column is stored as s * v with a scalar s, its reciprocal r = 1 / s travels along.
+// Rotating x = sP P, y = sQ Q by (cos, sin) is exactly
+//     x' = (cos sP) [P - tan (sQ / sP) Q],     y' = (cos sQ) [Q + tan (sP / sQ) P],
+// so the 16 rows cost two FMAs each instead of two multiplies and two FMAs, and the factor cos goes into the scales
+// (FP64 instructions are what the score warps wait for: profiles/r01_v7_resolve_ncu.md).  The scales are folded
+// back into the columns once per sweep (fold_scales), so they stay within a few orders of magnitude of 1.
+__device__ __forceinline__ void fold_scales(double (&P)[16], double (&Q)[16], double &sP, double &rP, double &sQ, double &rQ)
+{
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { P[r] *= sP; Q[r] *= sQ; }
+    sP = 1.0; rP = 1.0; sQ = 1.0; rQ = 1.0;
+}
+
+__device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], double &sP, double &rP, double &sQ, double &rQ,
+                                              double &nP, double &nQ, double tiny, bool &big, bool force = false,
+                                              bool enable = true)
 {
     double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
 #pragma unroll
@@ -678,7 +692,7 @@ __device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], 
         g0 = fma(P[r], Q[r], g0); g1 = fma(P[r + 1], Q[r + 1], g1);
         g2 = fma(P[r + 2], Q[r + 2], g2); g3 = fma(P[r + 3], Q[r + 3], g3);
     }
-    const double ga = (g0 + g1) + (g2 + g3);
+    const double ga = (sP * sQ) * ((g0 + g1) + (g2 + g3));
     const double ab = nP * nQ, gg = ga * ga;
     if (force || (enable && nP > tiny && nQ > tiny && gg > kTau2 * ab)) {
         big |= gg > kStop2 * ab;
@@ -700,13 +714,18 @@ __device__ __forceinline__ void jacobi_rotate(double (&P)[16], double (&Q)[16], 
         const double f = fma(e, fma(0.375, e, -0.5), 1.0);               // (1 + e)^(-1/2) to O(e^3)
         cs *= f;
         sn *= f;
+        double ic = rc;                                                  // 1 / cos: two Newton steps from the approximation
+        ic = ic * fma(-cs, ic, 2.0);
+        ic = ic * fma(-cs, ic, 2.0);
+        const double t = sn * ic;                                        // tan
+        const double al = t * (sQ * rP), be = t * (sP * rQ);
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const double p = P[r], qq = Q[r];
-            P[r] = fma(cs, p, -(sn * qq));
-            Q[r] = fma(sn, p, cs * qq);
+            P[r] = fma(-al, qq, p);
+            Q[r] = fma(be, p, qq);
         }
-        const double t = sn * rc;                                        // tan ~ sin / cos (only feeds the cached norms)
+        sP *= cs; sQ *= cs; rP *= ic; rQ *= ic;
         const double tg = t * ga;
         nP -= tg;
         nQ += tg;
@@ -838,12 +857,14 @@ __device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int l
         }
         __syncwarp();
     }
-    double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][9 double2] (144 B stride)
+    double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][11 double2] (176 B stride: conflict-free)
 
     // A matrix stops rotating after ITS last sweep, whatever the other two still need: every flattening then goes
     // through exactly the same arithmetic here and in svd_scores4, and the three kernel variants agree bit for bit.
     bool gdone = lane >= 24;
+    double sP = 1.0, rP = 1.0, sQ = 1.0, rQ = 1.0;   // column scales of the self-scaling rotations and their reciprocals
     for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+        fold_scales(P, Q, sP, rP, sQ, rQ);
         double nP = 0.0, nQ = 0.0;                   // refresh the cached squared norms
 #pragma unroll
         for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
@@ -851,12 +872,12 @@ __device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int l
 #pragma unroll 1
         for (int g = 8; g >= 1; g >>= 1) {
             for (int r = 0; r < g; ++r) {
-                jacobi_rotate(P, Q, nP, nQ, tiny, big, (debug & 64u) != 0, !gdone);
+                jacobi_rotate(P, Q, sP, rP, sQ, rQ, nP, nQ, tiny, big, (debug & 64u) != 0, !gdone);
                 if (r + 1 < g && !(debug & 16u)) {   // Q moves one lane down inside its group of g
                     const int src = (lane & ~(g - 1)) | ((lane + 1) & (g - 1));
 #pragma unroll
                     for (int k = 0; k < 16; ++k) Q[k] = __shfl_sync(kFull, Q[k], src);
-                    nQ = __shfl_sync(kFull, nQ, src);
+                    nQ = __shfl_sync(kFull, nQ, src); sQ = __shfl_sync(kFull, sQ, src); rQ = __shfl_sync(kFull, rQ, src);
                 }
             }
             if (g > 1 && !(debug & 16u)) {
@@ -864,26 +885,26 @@ __device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int l
                 // upper lanes keep Q and take the partner's Q as P
                 const int h = g >> 1;
                 const bool lower = (lane & (g - 1)) < h;
-                double2 *mine = xbuf + lane * 9;
+                double2 *mine = xbuf + lane * 11;
                 if (lower) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) mine[k] = make_double2(Q[2 * k], Q[2 * k + 1]);
-                    mine[8] = make_double2(nQ, 0.0);
+                    mine[8] = make_double2(nQ, sQ); mine[9] = make_double2(rQ, 0.0);
                 } else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) mine[k] = make_double2(P[2 * k], P[2 * k + 1]);
-                    mine[8] = make_double2(nP, 0.0);
+                    mine[8] = make_double2(nP, sP); mine[9] = make_double2(rP, 0.0);
                 }
                 __syncwarp();
-                const double2 *theirs = xbuf + (lower ? lane + h : lane - h) * 9;
+                const double2 *theirs = xbuf + (lower ? lane + h : lane - h) * 11;
                 if (lower) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { const double2 x = theirs[k]; Q[2 * k] = x.x; Q[2 * k + 1] = x.y; }
-                    nQ = theirs[8].x;
+                    nQ = theirs[8].x; sQ = theirs[8].y; rQ = theirs[9].x;
                 } else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { const double2 x = theirs[k]; P[2 * k] = x.x; P[2 * k + 1] = x.y; }
-                    nP = theirs[8].x;
+                    nP = theirs[8].x; sP = theirs[8].y; rP = theirs[9].x;
                 }
                 __syncwarp();
             }
@@ -896,6 +917,7 @@ __device__ __noinline__ void svd_scores(const uint32_t *T, SvdScratch &sv, int l
 
     // singular values = column norms; sort descending per matrix by rank counting
     {
+        fold_scales(P, Q, sP, rP, sQ, rQ);
         double nP = 0.0, nQ = 0.0;
 #pragma unroll
         for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
@@ -1072,12 +1094,14 @@ __device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, 
             }
             __syncwarp();
         }
-        double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][9 double2] (144 B stride)
+        double2 *xbuf = reinterpret_cast<double2 *>(&sv.M[0][0][0]);   // [32 lanes][11 double2] (176 B stride: conflict-free)
 
         // A matrix stops rotating after ITS last sweep, whatever the other three of the pass still need: the result of a
         // quartet must not depend on which quartets happen to share its batch (run-to-run reproducibility).
         bool gdone = !act;
+        double sP = 1.0, rP = 1.0, sQ = 1.0, rQ = 1.0;   // column scales of the self-scaling rotations and their reciprocals
         for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+            fold_scales(P, Q, sP, rP, sQ, rQ);
             double nP = 0.0, nQ = 0.0;                   // refresh the cached squared norms
 #pragma unroll
             for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
@@ -1085,37 +1109,37 @@ __device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, 
 #pragma unroll 1
             for (int g = 8; g >= 1; g >>= 1) {
                 for (int r = 0; r < g; ++r) {
-                    jacobi_rotate(P, Q, nP, nQ, tiny, big, false, !gdone);
+                    jacobi_rotate(P, Q, sP, rP, sQ, rQ, nP, nQ, tiny, big, false, !gdone);
                     if (r + 1 < g) {                     // Q moves one lane down inside its group of g
                         const int src = (lane & ~(g - 1)) | ((lane + 1) & (g - 1));
 #pragma unroll
                         for (int k = 0; k < 16; ++k) Q[k] = __shfl_sync(kFull, Q[k], src);
-                        nQ = __shfl_sync(kFull, nQ, src);
+                        nQ = __shfl_sync(kFull, nQ, src); sQ = __shfl_sync(kFull, sQ, src); rQ = __shfl_sync(kFull, rQ, src);
                     }
                 }
                 if (g > 1) {
                     const int h = g >> 1;
                     const bool lower = (lane & (g - 1)) < h;
-                    double2 *mine = xbuf + lane * 9;
+                    double2 *mine = xbuf + lane * 11;
                     if (lower) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) mine[k] = make_double2(Q[2 * k], Q[2 * k + 1]);
-                        mine[8] = make_double2(nQ, 0.0);
+                        mine[8] = make_double2(nQ, sQ); mine[9] = make_double2(rQ, 0.0);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) mine[k] = make_double2(P[2 * k], P[2 * k + 1]);
-                        mine[8] = make_double2(nP, 0.0);
+                        mine[8] = make_double2(nP, sP); mine[9] = make_double2(rP, 0.0);
                     }
                     __syncwarp();
-                    const double2 *theirs = xbuf + (lower ? lane + h : lane - h) * 9;
+                    const double2 *theirs = xbuf + (lower ? lane + h : lane - h) * 11;
                     if (lower) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { const double2 x = theirs[k]; Q[2 * k] = x.x; Q[2 * k + 1] = x.y; }
-                        nQ = theirs[8].x;
+                        nQ = theirs[8].x; sQ = theirs[8].y; rQ = theirs[9].x;
                     } else {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) { const double2 x = theirs[k]; P[2 * k] = x.x; P[2 * k + 1] = x.y; }
-                        nP = theirs[8].x;
+                        nP = theirs[8].x; sP = theirs[8].y; rP = theirs[9].x;
                     }
                     __syncwarp();
                 }
@@ -1127,6 +1151,7 @@ __device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, 
 
         // singular values = column norms; sort descending per matrix by rank counting
         {
+            fold_scales(P, Q, sP, rP, sQ, rQ);
             double nP = 0.0, nQ = 0.0;
 #pragma unroll
             for (int r = 0; r < 16; ++r) { nP = fma(P[r], P[r], nP); nQ = fma(Q[r], Q[r], nQ); }
