@@ -1544,8 +1544,14 @@ __device__ unsigned long long g_mma_clk[8];         // count: slot wait, stage 2
 #define TQ_MMA_STAGES 4                       // cp.async ring depth of the tensor-core kernel's count warps
 #endif
 static constexpr int kMStages = TQ_MMA_STAGES;
+#ifndef TQ_MMA_SCALES
+#define TQ_MMA_SCALES 4                       // 4: masks 0x01010101 << v on the word and on the word >> 4 (32 accumulator registers);
+                                              // 8: masks << 0..7 straight from the planes, no shift (64 accumulator registers)
+#endif
+static constexpr int kScales = TQ_MMA_SCALES;
 static constexpr int kPStride = 34;                 // words per plane row of the per-warp tile copy
-static constexpr uint32_t kMmaFlushEvery = 16384;   // tile products between accumulator flushes: 16384 * 1024 * 4^3 < 2^31
+static constexpr uint32_t kMmaFlushEvery = kScales == 8 ? 512 : 16384;   // tile products between accumulator flushes: 16384 * 1024 * 4^3
+                                                    // (512 * 128 * 4^7 with eight scales) < 2^31
                                                     // (env TQ_MMA_FLUSH lowers it so that tests reach the flush path)
 
 __device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
@@ -1572,7 +1578,7 @@ __device__ __forceinline__ MmaLanePtrs mma_lane_ptrs(uint32_t *P, int lane)
 
 __device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
                                                const uint32_t (&MC)[4], const uint32_t (&MD)[4],
-                                               const MmaLanePtrs &lp, int (&acc)[4][2][4])
+                                               const MmaLanePtrs &lp, int (&acc)[kScales][2][4])
 {
     __syncwarp();                                    // the previous tile's reads are over
 #pragma unroll
@@ -1592,6 +1598,15 @@ __device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const ui
         const uint2 c0 = *reinterpret_cast<const uint2 *>(pa + 8 * kPStride + 2 * i);
         const uint2 c1 = *reinterpret_cast<const uint2 *>(pa + 10 * kPStride + 2 * i);
         const uint2 d = *reinterpret_cast<const uint2 *>(pb + 8 * kPStride + 2 * i);
+#if TQ_MMA_SCALES == 8
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {                 // three-input LOP3 straight from the planes: a & b & mask
+            const uint32_t msk = 0x01010101u << v;
+            const uint32_t f0 = a0.x & b.x & msk, f1 = a1.x & b.x & msk, f2 = a0.y & b.y & msk, f3 = a1.y & b.y & msk;
+            imma_u8(acc[v][0], f0, f1, f2, f3, c0.x & d.x & msk, c0.y & d.y & msk);
+            imma_u8(acc[v][1], f0, f1, f2, f3, c1.x & d.x & msk, c1.y & d.y & msk);
+        }
+#else
         uint32_t x[2][4], y[2][4];    // x: rows g / g+8 of word W, then of word W';  y: column g of half 0 (W, W'), of half 1 (W, W')
         x[0][0] = a0.x & b.x; x[0][1] = a1.x & b.x; x[0][2] = a0.y & b.y; x[0][3] = a1.y & b.y;
         y[0][0] = c0.x & d.x; y[0][1] = c0.y & d.y; y[0][2] = c1.x & d.x; y[0][3] = c1.y & d.y;
@@ -1606,12 +1621,13 @@ __device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const ui
                 imma_u8(acc[v][0], f0, f1, f2, f3, y[s][0] & msk, y[s][1] & msk);
                 imma_u8(acc[v][1], f0, f1, f2, f3, y[s][2] & msk, y[s][3] & msk);
             }
+#endif
     }
 }
 
 // Add the accumulated counts into T and clear the accumulators.  Lane (g, j) holds rows g and g + 8,
 // columns 2j and 2j + 1 of each column half: no cross-lane step.
-__device__ __forceinline__ void flush_mma(int (&acc)[4][2][4], uint32_t *T, int lane)
+__device__ __forceinline__ void flush_mma(int (&acc)[kScales][2][4], uint32_t *T, int lane)
 {
     const int g = lane >> 2, j = lane & 3;
 #pragma unroll
@@ -1620,7 +1636,7 @@ __device__ __forceinline__ void flush_mma(int (&acc)[4][2][4], uint32_t *T, int 
         for (int rr = 0; rr < 2; ++rr) {
             uint32_t c0 = 0u, c1 = 0u;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < kScales; ++v) {
                 c0 += (uint32_t)acc[v][h][2 * rr] >> (2 * v);
                 c1 += (uint32_t)acc[v][h][2 * rr + 1] >> (2 * v);
                 acc[v][h][2 * rr] = 0; acc[v][h][2 * rr + 1] = 0;
@@ -1647,9 +1663,9 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
                                                   )
 {
     static_assert((kMStages & (kMStages - 1)) == 0, "ring depth must be a power of two");
-    int acc[4][2][4];
+    int acc[kScales][2][4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v)
+    for (int v = 0; v < kScales; ++v)
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
