@@ -163,11 +163,18 @@ int tq_ctx_last_traffic(const tq_ctx *ctx, int64_t out[2]);
  *   from the parsed TSV, run_inference.py:262-297).
  * tq_format_qmc: lines "a,b|c,d:%.5f" (run_inference.py:305) for n quartets whose tips are already in
  *   split order; returns bytes written (>= 128 bytes per line suffices).
+ * tq_qmc_weights: the quartets that pass the filters (nsnps >= max(1, min_snps), ratio >= min_ratio;
+ *   run_inference.py:258,275,300), their tips in split order a,b|c,d and their wQMC weight (strategy 0: 1,
+ *   1: mean of the two largest scores, 2: that mean over the smallest, 3: 1 - smallest / sum; :280-297), computed
+ *   from the scores as they read back from the TSV.  tips_out u32[m][4] and weight_out f64[m] receive the kept
+ *   rows in order; returns their number, TQ_EINVAL for a score that is not a finite non-negative number.
  */
 int64_t tq_format_tsv(const uint32_t *quartets, const uint32_t *rstat, const double *rscor, int64_t m,
                       char *out, int64_t cap);
 int     tq_round_scores(const double *rscor, int64_t n, double *out);
 int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, char *out, int64_t cap);
+int64_t tq_qmc_weights(const uint32_t *quartets, const uint32_t *rstat, const double *rscor, int64_t m, int weights,
+                       int64_t min_snps, double min_ratio, uint32_t *tips_out, double *weight_out);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): pipe micro-benchmarks on `device`.

@@ -105,6 +105,42 @@ int tq_round_scores(const double *rscor, int64_t n, double *out)
     return TQ_OK;
 }
 
+int64_t tq_qmc_weights(const uint32_t *quartets, const uint32_t *rstat, const double *rscor, int64_t m, int weights,
+                       int64_t min_snps, double min_ratio, uint32_t *tips_out, double *weight_out)
+{
+    if (m < 0 || weights < 0 || weights > 3 || (m > 0 && (!quartets || !rstat || !rscor || !tips_out || !weight_out)))
+        return TQ_EINVAL;
+    static const int order[3][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};   // split -> a,b|c,d (run_inference.py:41-45)
+    if (min_snps < 1) min_snps = 1;
+    int64_t n = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        double sc[3];
+        for (int k = 0; k < 3; ++k) {
+            const double x = rscor[3 * i + k];
+            if (!printable(x)) return TQ_EINVAL;                       // the caller's numpy path handles odd values
+            sc[k] = (double)exact_round(x, 6) / 1.0e6;                 // the score as the reference reads it back from the TSV
+        }
+        double weight = 1.0, ratio = 1.0;
+        if (weights) {
+            const double lo_ab = sc[0] < sc[1] ? sc[0] : sc[1], hi_ab = sc[0] < sc[1] ? sc[1] : sc[0];
+            const double smin = lo_ab < sc[2] ? lo_ab : sc[2];
+            const double smax = hi_ab > sc[2] ? hi_ab : sc[2];
+            const double m2 = hi_ab < sc[2] ? hi_ab : sc[2];
+            const double smid = lo_ab > m2 ? lo_ab : m2;
+            const double smean = (smid + smax) / 2.0;                  // mean of the two largest (:281-283)
+            ratio = (smin == 0.0) ? 1.0 : smean / smin;
+            const double third = 1.0 - smin / ((smin + smid) + smax);
+            weight = weights == 1 ? smean : weights == 2 ? ratio : third;
+        }
+        if ((int64_t)rstat[2 * i + 1] < min_snps || ratio < min_ratio) continue;   // filters :258, :275, :300
+        const uint32_t best = rstat[2 * i] < 2u ? rstat[2 * i] : 2u;
+        for (int k = 0; k < 4; ++k) tips_out[4 * n + k] = quartets[4 * i + order[best][k]];
+        weight_out[n] = weight;
+        ++n;
+    }
+    return n;
+}
+
 int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, char *out, int64_t cap)
 {
     if (n < 0 || (n > 0 && (!tips || !weight || !out))) return TQ_EINVAL;

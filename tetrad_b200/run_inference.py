@@ -63,24 +63,54 @@ def resample_arrays(seqarr: np.ndarray, spans: np.ndarray, rng: np.random.Genera
 # ----------------------------------------------------------------------------------------------
 # result sink (reference :232-247)
 # ----------------------------------------------------------------------------------------------
+_SINK_CHUNK = 1 << 16          # rows formatted per C call
+_sink_pool = None
+
+
+def _format_parallel(call, nrows: int, row_bytes: int):
+    """Yield, in row order, the bytes ``call(lo, hi, buf)`` formats for consecutive row ranges.  The C formatters
+    run without the GIL (ctypes), so the ranges are formatted on a small thread pool: at C3/C4 sizes the host
+    sink, not the GPU, was what a replicate waited for."""
+    import ctypes
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    global _sink_pool
+    if _sink_pool is None:
+        _sink_pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1)),
+                                        thread_name_prefix="tetrad-sink")
+
+    def work(lo):
+        hi = min(nrows, lo + _SINK_CHUNK)
+        buf = ctypes.create_string_buffer(row_bytes * (hi - lo))
+        n = call(lo, hi, buf)
+        if n < 0:
+            from . import _lib
+            _lib.check(int(n))
+        return ctypes.string_at(buf, n)
+
+    starts = range(0, nrows, _SINK_CHUNK)
+    if nrows <= _SINK_CHUNK:
+        yield from (work(lo) for lo in starts)
+    else:
+        yield from _sink_pool.map(work, starts)
+
+
 def write_quartets_tsv(path: Path, quartets, rstat, rscor, append: bool = False) -> None:
     """``t0 t1 t2 t3 s0 s1 s2 best nsnps``, tab-separated, scores ``%.6f``, no header: the line
     format pandas produces at run_inference.py:232-234.  Formatted in C (``tq_format_tsv``)."""
-    import ctypes
     from . import _lib
     lib = _lib.load()
     quartets = np.ascontiguousarray(quartets, dtype=np.uint32).reshape(-1, 4)
     rstat = np.ascontiguousarray(rstat, dtype=np.uint32).reshape(-1, 2)
     rscor = np.ascontiguousarray(rscor, dtype=np.float64).reshape(-1, 3)
-    step = 1 << 17
-    buf = ctypes.create_string_buffer(160 * min(step, max(1, len(quartets))))
+    qp, sp, cp = quartets.ctypes.data, rstat.ctypes.data, rscor.ctypes.data
+
+    def call(lo, hi, buf):
+        return lib.tq_format_tsv(qp + 16 * lo, sp + 8 * lo, cp + 24 * lo, hi - lo, buf, len(buf))
+
     with open(path, "ab" if append else "wb") as out:
-        for lo in range(0, len(quartets), step):
-            q, st, sc = quartets[lo: lo + step], rstat[lo: lo + step], rscor[lo: lo + step]
-            n = lib.tq_format_tsv(q.ctypes.data, st.ctypes.data, sc.ctypes.data, len(q), buf, len(buf))
-            if n < 0:
-                _lib.check(int(n))
-            out.write(buf.raw[:n])
+        for piece in _format_parallel(call, len(quartets), 160):
+            out.write(piece)
 
 
 def qmc_weights(quartets, rstat, rscor, weights: int, min_snps: int = 0, min_ratio: float = 1.0):
@@ -94,21 +124,39 @@ def qmc_weights(quartets, rstat, rscor, weights: int, min_snps: int = 0, min_rat
     quartets = np.ascontiguousarray(quartets, dtype=np.uint32).reshape(-1, 4)
     rstat = np.ascontiguousarray(rstat, dtype=np.uint32).reshape(-1, 2)
     rscor = np.ascontiguousarray(rscor, dtype=np.float64).reshape(-1, 3)
+    # one pass in C (tq_qmc_weights); scores that are not finite non-negative numbers take the numpy path below
+    tips_out = np.empty((len(quartets), 4), dtype=np.uint32)
+    weight_out = np.empty(len(quartets), dtype=np.float64)
+    n = lib.tq_qmc_weights(quartets.ctypes.data, rstat.ctypes.data, rscor.ctypes.data, len(quartets), int(weights),
+                           int(min_snps), float(min_ratio), tips_out.ctypes.data, weight_out.ctypes.data)
+    if n >= 0:
+        return tips_out[:n], weight_out[:n]
     scores = np.empty_like(rscor)
     _lib.check(lib.tq_round_scores(rscor.ctypes.data, rscor.size, scores.ctypes.data))
     min_snps = max(1, min_snps)
-    best = np.minimum(rstat[:, 0].astype(np.int64), 2)
-    tips = np.take_along_axis(quartets, TIDXS[best].astype(np.int64), axis=1)
-    srt = np.sort(scores, axis=1)
+    best = np.minimum(rstat[:, 0], 2)
+    # tips in split order a,b|c,d = quartets[:, TIDXS[best]] (column selects instead of a fancy-index gather)
+    t1, t2, t3 = quartets[:, 1], quartets[:, 2], quartets[:, 3]
+    is0, is1 = best == 0, best == 1
+    tips = np.empty_like(quartets)
+    tips[:, 0] = quartets[:, 0]
+    tips[:, 1] = np.where(is0, t1, np.where(is1, t2, t3))
+    tips[:, 2] = np.where(is0, t2, t1)
+    tips[:, 3] = np.where(is0 | is1, t3, t2)
     if not weights:
         weight = np.ones(len(quartets))
         ratio = np.ones(len(quartets))
     else:
-        smean = srt[:, 1:].mean(axis=1)
-        smin = srt[:, 0]
+        # the sorted scores (reference :280) without a generic sort: min, median and max of three, exactly
+        a, b, c = scores[:, 0], scores[:, 1], scores[:, 2]
+        lo_ab, hi_ab = np.minimum(a, b), np.maximum(a, b)
+        smin = np.minimum(lo_ab, c)
+        smax = np.maximum(hi_ab, c)
+        smid = np.maximum(lo_ab, np.minimum(hi_ab, c))
+        smean = (smid + smax) / 2.0                      # == srt[:, 1:].mean(axis=1)
         with np.errstate(divide="ignore", invalid="ignore"):
             ratio = np.where(smin == 0, 1.0, smean / np.where(smin == 0, 1.0, smin))
-            third = 1.0 - smin / srt.sum(axis=1)
+            third = 1.0 - smin / ((smin + smid) + smax)  # == srt.sum(axis=1), added in sorted order
         weight = {1: smean, 2: ratio, 3: third}[weights]
     keep = (rstat[:, 1] >= min_snps) & ~(ratio < min_ratio)
     return np.ascontiguousarray(tips[keep], dtype=np.uint32), np.ascontiguousarray(weight[keep], dtype=np.float64)
@@ -116,19 +164,16 @@ def qmc_weights(quartets, rstat, rscor, weights: int, min_snps: int = 0, min_rat
 
 def format_qmc_lines(tips: np.ndarray, weight: np.ndarray) -> bytes:
     """``a,b|c,d:%.5f`` lines (run_inference.py:305), formatted in C (``tq_format_qmc``)."""
-    import ctypes
     from . import _lib
     lib = _lib.load()
-    out, step = [], 1 << 17
-    buf = ctypes.create_string_buffer(128 * min(step, max(1, len(tips))))
-    for lo in range(0, len(tips), step):
-        t = np.ascontiguousarray(tips[lo: lo + step], dtype=np.uint32)
-        w = np.ascontiguousarray(weight[lo: lo + step], dtype=np.float64)
-        n = lib.tq_format_qmc(t.ctypes.data, w.ctypes.data, len(t), buf, len(buf))
-        if n < 0:
-            _lib.check(int(n))
-        out.append(buf.raw[:n])
-    return b"".join(out)
+    tips = np.ascontiguousarray(tips, dtype=np.uint32).reshape(-1, 4)
+    weight = np.ascontiguousarray(weight, dtype=np.float64)
+    tp, wp = tips.ctypes.data, weight.ctypes.data
+
+    def call(lo, hi, buf):
+        return lib.tq_format_qmc(tp + 16 * lo, wp + 8 * lo, hi - lo, buf, len(buf))
+
+    return b"".join(_format_parallel(call, len(tips), 128))
 
 
 def read_quartets_tsv(path: Path):
