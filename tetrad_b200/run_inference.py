@@ -332,39 +332,56 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
     elif exhaustive:
         full = combinations.all_quartets(proj.nsamples)
     import time
+    on_device = device_bootstrap and hasattr(resolver, "load_bootstrap")
+
+    def draw_replicate(idx):
+        """Every draw replicate ``idx`` takes from the project's generator, in the reference's order (its quartet
+        generator is lazy: the quartet draw happens after the resampling draws), and the generator state after
+        them.  Host work only, so that it can run while the GPU resolves the previous replicate."""
+        boot = host_arrays = ranks = drawn = None
+        if idx and on_device:
+            boot = draw_bootstrap(arrays["spans"], rng)
+        elif idx:
+            host_arrays = resample_arrays(arrays["seqarr"], arrays["spans"], rng)
+        if full is None and gpu_index is not None:              # same draw as the reference, unranked on the GPU later
+            from math import comb
+            ranks = np.random.default_rng(rng).choice(comb(proj.nsamples, 4), size=proj.nqrts, replace=False)
+        elif full is None:
+            drawn = combinations.random_quartets(proj.nsamples, proj.nqrts, rng)
+        return dict(boot=boot, host_arrays=host_arrays, ranks=ranks, drawn=drawn, state=RNGStateModel.from_rng(rng))
+
+    draws = draw_replicate(proj.bootstrap_idx) if proj.bootstrap_idx <= nboots else None
     while proj.bootstrap_idx <= nboots:
         t_start = time.perf_counter()
-        # the reference's quartet generator is lazy: its draw happens after the resampling draws
-        on_device = device_bootstrap and hasattr(resolver, "load_bootstrap")
-        if proj.bootstrap_idx and on_device:
-            lidxs, seed_shuffle, seed_ambig = draw_bootstrap(arrays["spans"], rng)
+        if draws["boot"] is not None:
+            lidxs, seed_shuffle, seed_ambig = draws["boot"]
             seq = getattr(resolver, "seqarr_dev", None)
             resolver.load_bootstrap(seq if seq is not None else arrays["seqarr"], arrays["spans"], lidxs,
                                     seed_shuffle, seed_ambig)
-        elif proj.bootstrap_idx:
-            resolver.load(*resample_arrays(arrays["seqarr"], arrays["spans"], rng))
+        elif draws["host_arrays"] is not None:
+            resolver.load(*draws["host_arrays"])
         else:
             resolver.load(arrays["tmparr"], arrays["tmpmap"])
         if full is not None:
             quartets, q_dev = full, full_dev
-        elif gpu_index is not None:                                 # same draw as the reference, unranked on the GPU
-            from math import comb
-            ranks = np.random.default_rng(rng).choice(comb(proj.nsamples, 4), size=proj.nqrts, replace=False)
-            q_dev = combinations.device_quartets(proj.nsamples, gpu_index, ranks=ranks)
+        elif draws["ranks"] is not None:
+            q_dev = combinations.device_quartets(proj.nsamples, gpu_index, ranks=draws["ranks"])
             quartets = q_dev.cpu().numpy().view(np.uint32)
         else:
-            quartets, q_dev = combinations.random_quartets(proj.nsamples, proj.nqrts, rng), None
+            quartets, q_dev = draws["drawn"], None
         if q_dev is None:
             q_dev = torch.from_numpy(quartets.view(np.int32))
             if hasattr(resolver, "device"):
                 q_dev = q_dev.to(resolver.device)
         t_prep = time.perf_counter()
         out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
+        idx = proj.bootstrap_idx
+        rng_state = draws["state"]                       # generator state after this replicate's draws
+        # the next replicate's host draws (rng.choice over the loci and over the quartet ranks) run while the GPU resolves
+        draws = draw_replicate(idx + 1) if idx + 1 <= nboots else None
         if hasattr(resolver, "device"):
             torch.cuda.synchronize(resolver.device)
         t_gpu = time.perf_counter()
-        idx = proj.bootstrap_idx
-        rng_state = RNGStateModel.from_rng(rng)          # generator state after this replicate's draws
         if pending is not None:
             pending.result()                               # sinks finish (and checkpoint) in replicate order
             pending = None
