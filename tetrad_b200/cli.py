@@ -52,6 +52,28 @@ def _legacy(argv) -> int:
     return 0
 
 
+def _init_distributed(device: int):
+    """Under ``torchrun`` (one process per GPU) every rank loads the same project, takes the same draws from the
+    project's generator, resolves its contiguous share of every replicate's quartets and rank 0 gathers them over
+    NCCL and writes the files (``sharding.resolve_sharded``; the reference farms chunks out over ipyparallel,
+    run_inference.py:184-251).  Returns (device index, whether a process group was created here)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return device, False
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return int(os.environ.get("LOCAL_RANK", device)), False
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if dist.get_rank() != 0:
+        logging.getLogger().setLevel(logging.WARNING)       # one log stream, rank 0's
+    return local, True
+
+
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     if argv and argv[0] == "-i" or (len(argv) > 1 and "-i" in argv and argv[0] not in ("init", "run")):
@@ -69,7 +91,13 @@ def main(argv=None) -> int:
         return 0
     if args.subcommand == "run":
         from .run_inference import run_inference
-        run_inference(Project.load_json(args.json), args.cores, args.boots, device=args.device)
+        device, group = _init_distributed(args.device)
+        try:
+            run_inference(Project.load_json(args.json), args.cores, args.boots, device=device)
+        finally:
+            if group:
+                import torch.distributed as dist
+                dist.destroy_process_group()
         return 0
     _parser().print_help()
     return 2
