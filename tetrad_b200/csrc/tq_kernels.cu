@@ -1,10 +1,26 @@
 // Hand-written sm_100a kernels of the quartet-resolution hot path.
 //
-//   pack_kernel     K1  u8 tmparr -> locus-tiled one-hot A/C/G/T bit-planes
-//   resolve_kernel  K3+K4  per quartet: select one SNP per locus, 256 site-pattern counts by
-//                   AND + POPC, three 16x16 one-sided Jacobi SVDs in FP64, rank / minrank /
-//                   tail score / argmin -- one warp per quartet, nothing but the result leaves
-//                   the SM.
+//   pack_kernel            K1     u8 tmparr -> locus-tiled one-hot A/C/G/T bit-planes
+//   boot_columns_kernel,   K2/K5  bootstrap replicates on the device: Philox column orders per locus instance, planes packed
+//   pack_gather_kernel            straight from the resident ASCII seqarr with IUPAC cells resolved by Philox coins
+//   unrank_kernel                 lexicographic rank -> quartet (combinations.py:94-106)
+//   resolve_mma_kernel     K3+K4  the kernel large launches run: count warps select one SNP per locus (stage 1) and form the
+//                                 256 site-pattern counts on the integer tensor cores (stage 2: IMMA.16832.U8.U8 on bit planes
+//                                 unpacked by one LOP3 per four loci); score warps take four quartets at a time through three
+//                                 FP64 QR + one-sided-Jacobi passes of four 16x16 flattenings; rank / minrank / tail score /
+//                                 argmin; only the result leaves the SM
+//   resolve_kernel                same result, one warp per quartet, counts by AND + POPC with the counters in tensor memory
+//                                 (tcgen05.alloc/ld/st): what small launches run
+//   resolve_ws_kernel             warp-specialised POPC variant (round-1 v5), selectable
+//   pipe_kernel, mix_kernel, imma_rate_kernel, copy_kernel   roofline denominators measured on the box (tq_microbench)
+//
+// launch_resolve picks the resolve kernel by launch size; tq_set_option("kernel", ..) / TQ_KERNEL force one.  All three
+// give bit-identical results.  Build switches (all default to the shipped configuration; profiles/ cites the measurements):
+//   TQ_MMA_NC / TQ_MMA_NS / TQ_MMA_CTAS  warp mix of resolve_mma_kernel       TQ_MMA_STAGES  cp.async ring depth
+//   TQ_MMA_TMA      ring filled by TMA bulk copies        TQ_MMA_SCALES  4 | 8 mask scales in stage 2
+//   TQ_MMA_SPLIT, TQ_MMA_ROLEMASK  placement of the roles over the four schedulers
+//   TQ_MMA_TIMERS   clock64 phase accumulators           TQ_DBG_NO_LOAD / _NO_S1 / _NO_S2, TQ_NO_SVD, TQ_COUNT_TILES  knock-outs
+//   TQ_STOP2, TQ_TAU2  Jacobi stopping / rotation thresholds       TQ_TMEM, TQ_WS_DEC/INC, TQ_MIN_CTAS  the POPC kernels
 //
 // Reference semantics restated here (paths relative to the reference repo):
 //   tetrad/src/resolve_quartets.py:212-221  gather, missing mask, invariant mask
