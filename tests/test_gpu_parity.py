@@ -205,6 +205,14 @@ def test_tetrad_facade_and_cli_end_to_end(tb, oracle, tmp_path):
     assert (nsnps == ostat[:, 1]).all() and (best == ostat[:, 0]).all()
     np.testing.assert_allclose(scores, oscor, rtol=1e-5, atol=1e-6)      # TSV carries 6 decimals
     assert (tmp_path / "w" / "fac.quartets_1.tsv").exists() and (tmp_path / "w" / "fac.qmc_in.txt").exists()
+    # save_invariants (deprecated API option): the count matrices of every replicate
+    tet2 = tb.Tetrad("inv", str(tmp_path / "in.npz"), workdir=str(tmp_path / "w2"), nquartets=0, nboots=0, seed=7,
+                     save_invariants=True)
+    tet2.run()
+    inv = np.load(tmp_path / "w2" / "inv.invariants_0.npy")
+    _, _, _, det = oracle.new_infer_resolved_quartets(arrays["tmparr"], arrays["tmpmap"], q.astype(np.uint32), True,
+                                                      return_details=True)
+    assert inv.dtype == np.uint32 and (inv == det["mats"][:, 0]).all()
     # CLI: init + run (full mode: the live CLI's default is subsample_snps=False)
     assert cli.main(["init", str(tmp_path / "in.npz"), "-n", "c", "-w", str(tmp_path / "c"), "-r", "3"]) == 0
     assert cli.main(["run", str(tmp_path / "c" / "c.json"), "-c", "4", "-b", "0"]) == 0

@@ -295,17 +295,22 @@ def draw_bootstrap(spans: np.ndarray, rng: np.random.Generator):
 
 
 def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int = 0, resolver=None,
-                  device_bootstrap: bool = True, overlap_sink: bool = True) -> None:
+                  device_bootstrap: bool = True, overlap_sink: bool = True, save_invariants: bool = False) -> None:
     """Resolve replicate 0 (original data) and ``nboots`` bootstrap replicates, checkpointing
     after each one exactly like the reference (:405-407).  ``ncores`` is accepted for CLI
     compatibility and ignored: the work runs on the GPU(s).  ``resolver`` (tests) overrides the
     engine: any object with ``load(tmparr, tmpmap)`` and ``resolve(quartets, subsample)``.
     With ``device_bootstrap`` (default) and an engine that has ``load_bootstrap``, replicates >= 1
     are shuffled, ambiguity-resolved and packed on the GPU from the resident ``seqarr``; otherwise
-    the host builds ``tmparr``/``tmpmap`` (``resample_arrays``) and the engine packs them."""
+    the host builds ``tmparr``/``tmpmap`` (``resample_arrays``) and the engine packs them.
+    ``save_invariants`` keeps every replicate's site-pattern count matrices, the deprecated API's option
+    (deprecated/distributor.py:231-257 stores them as ``invariants/boot{k}`` u16[nquartets,16,16] in its HDF5):
+    here ``{name}.invariants_{rep}.npy``, u32[nquartets,16,16] (= ``mats[0]``; u32 because counts pass 65 535)."""
     import torch
     import torch.distributed as dist
     from . import sharding
+    if save_invariants and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        raise NotImplementedError("save_invariants is a single-process option (1 KB per quartet is not gathered)")
 
     arrays = database.read_arrays(proj.database_file, ["seqarr", "spans", "tmparr", "tmpmap"])
     if resolver is None:
@@ -374,7 +379,12 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
             if hasattr(resolver, "device"):
                 q_dev = q_dev.to(resolver.device)
         t_prep = time.perf_counter()
-        out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
+        invariants = None
+        if save_invariants:
+            rstat_d, rscor_d, counts_d, _ = resolver.resolve(q_dev, proj.subsample_snps, want_counts=True)
+            out, invariants = (rstat_d, rscor_d), counts_d
+        else:
+            out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
         idx = proj.bootstrap_idx
         rng_state = draws["state"]                       # generator state after this replicate's draws
         # the next replicate's host draws (rng.choice over the loci and over the quartet ranks) run while the GPU resolves
@@ -389,6 +399,9 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
             rstat, rscor = out
             # D2H here (the GPU is idle anyway until the next launch); formatting, wQMC and the
             # checkpoint run on a worker thread while the next replicate is resolved
+            if invariants is not None:
+                np.save(proj.workdir / f"{proj.name}.invariants_{idx}.npy",
+                        invariants.cpu().numpy().view(np.uint32).reshape(-1, 16, 16))
             job = (idx, quartets, rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy(), rng_state)
             pending = pool.submit(_sink_replicate, proj, *job) if pool is not None else _sink_replicate(proj, *job)
             if pool is None:

@@ -59,5 +59,5 @@ class Tetrad:
             self.project.bootstrap_rng = None
             if self.project.boots_file.exists():
                 self.project.boots_file.unlink()
-        run_inference(self.project, ncores=0, nboots=self.nboots, device=device)
+        run_inference(self.project, ncores=0, nboots=self.nboots, device=device, save_invariants=self.save_invariants)
         return self
