@@ -1778,10 +1778,12 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
                                       (a.z & b.z & c.z & d.z) | (a.w & b.w & c.w & d.w);
                 const uint32_t sel = valid & ~same & ~taken;
                 taken |= sel;
-                MA[0] |= a.x & sel; MA[1] |= a.y & sel; MA[2] |= a.z & sel; MA[3] |= a.w & sel;
-                MB[0] |= b.x & sel; MB[1] |= b.y & sel; MB[2] |= b.z & sel; MB[3] |= b.w & sel;
-                MC[0] |= c.x & sel; MC[1] |= c.y & sel; MC[2] |= c.z & sel; MC[3] |= c.w & sel;
-                MD[0] |= d.x & sel; MD[1] |= d.y & sel; MD[2] |= d.z & sel; MD[3] |= d.w & sel;
+                // a selected column is complete, so the T plane of every tip is what the other three leave of `taken`:
+                // three merged planes per tip are updated per chunk, the fourth is derived once per tile
+                MA[0] |= a.x & sel; MA[1] |= a.y & sel; MA[2] |= a.z & sel;
+                MB[0] |= b.x & sel; MB[1] |= b.y & sel; MB[2] |= b.z & sel;
+                MC[0] |= c.x & sel; MC[1] |= c.y & sel; MC[2] |= c.z & sel;
+                MD[0] |= d.x & sel; MD[1] |= d.y & sel; MD[2] |= d.z & sel;
             } else {
                 // full mode (resolve_quartets.py:92-95): every complete column counts; the four
                 // invariant patterns aaaa are zeroed by the caller
@@ -1792,6 +1794,10 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
             }
         }
         if (kSubsample) {
+#ifndef TQ_DBG_NO_S1
+            MA[3] = taken & ~(MA[0] | MA[1] | MA[2]); MB[3] = taken & ~(MB[0] | MB[1] | MB[2]);
+            MC[3] = taken & ~(MC[0] | MC[1] | MC[2]); MD[3] = taken & ~(MD[0] | MD[1] | MD[2]);
+#endif
             TQM_T(ts2);
 #ifndef TQ_DBG_NO_S2
             count_tile_mma(MA, MB, MC, MD, lp, acc);
