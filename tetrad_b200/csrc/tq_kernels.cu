@@ -1552,6 +1552,9 @@ __device__ unsigned long long g_mma_clk[8];         // count: slot wait, stage 2
 #define TQ_MMA_SPLIT 0
 #endif
 
+#ifndef TQ_MMA_UNROLL
+#define TQ_MMA_UNROLL 1                       // unroll factor of the rank-chunk loop of stage 1
+#endif
 #ifndef TQ_MMA_TMA
 #define TQ_MMA_TMA 0                          // 1: count warps fill their ring with TMA bulk copies (cp.async.bulk + mbarrier); measured
                                               // slower than cp.async at this depth (7.76 vs 9.81 M quartets/s at C2), kept for reference
@@ -1560,6 +1563,7 @@ __device__ unsigned long long g_mma_clk[8];         // count: slot wait, stage 2
 #define TQ_MMA_STAGES 4                       // cp.async ring depth of the tensor-core kernel's count warps
 #endif
 static constexpr int kMStages = TQ_MMA_STAGES;
+static constexpr int kMUnroll = TQ_MMA_UNROLL;
 #ifndef TQ_MMA_SCALES
 #define TQ_MMA_SCALES 4                       // 4: masks 0x01010101 << v on the word and on the word >> 4 (32 accumulator registers);
                                               // 8: masks << 0..7 straight from the planes, no shift (64 accumulator registers)
@@ -1746,6 +1750,7 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
         uint32_t taken = 0u;
         uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
         uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
+#pragma unroll kMUnroll
         for (uint32_t k = 0; k < K; ++k, ++u) {
 #ifndef TQ_DBG_NO_LOAD
 #if TQ_MMA_TMA
