@@ -171,3 +171,25 @@ def test_replicate_loop_checkpoints_and_resumes(tmp_path, oracle):
     write_database.write_database(fresh)
     run_inference.run_inference(fresh, nboots=2, resolver=_OracleEngine())
     assert (tmp_path / "R.quartets_2.tsv").read_text() == (tmp_path / "S.quartets_2.tsv").read_text()
+
+
+@pytest.mark.parametrize("weights", [0, 1, 2, 3])
+def test_qmc_weights_c_pass_equals_numpy_formulation(weights):
+    """tq_qmc_weights (one C pass: scores through the TSV text, filters, tips in split order, weights) against the
+    numpy formulation of the same reference lines (run_inference.py:258-300), which a NaN score forces."""
+    from tetrad_b200 import run_inference as ri
+    rng = np.random.default_rng(weights)
+    m = 20000
+    q = np.sort(rng.integers(0, 60, (m, 4)), axis=1).astype(np.uint32)
+    rstat = np.stack([rng.integers(0, 3, m), rng.integers(0, 3000, m)], axis=1).astype(np.uint32)
+    rscor = rng.random((m, 3)) * rng.choice([1e-3, 1.0, 300.0], size=(m, 1))
+    rscor[::97, 0] = 0.0                                   # smallest score exactly zero: ratio defined as 1
+    rscor[::89] = rscor[::89, :1]                          # three equal scores
+    kw = dict(min_snps=100, min_ratio=1.1 if weights else 1.0)
+    tips, wt = ri.qmc_weights(q, rstat, rscor, weights, **kw)
+    q2 = np.vstack([q, [[0, 1, 2, 3]]]).astype(np.uint32)
+    r2 = np.vstack([rstat, [[0, 0]]]).astype(np.uint32)    # nsnps 0: filtered out again
+    s2 = np.vstack([rscor, [[np.nan, 1.0, 1.0]]])
+    tips2, wt2 = ri.qmc_weights(q2, r2, s2, weights, **kw)
+    assert 0 < len(tips) < m and len(tips2) == len(tips)
+    assert (tips == tips2).all() and wt.tobytes() == wt2.tobytes()
