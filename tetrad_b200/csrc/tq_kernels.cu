@@ -1443,7 +1443,12 @@ resolve_ws_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips
 #pragma unroll
             for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
             __syncwarp();
+#ifdef TQ_PHASE_TIMERS
+            long long ph_unused[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // the phase timers report the homogeneous kernel only
+            if (!bad) count_quartet<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], T, lane, 0u, tacc, ph_unused);
+#else
             if (!bad) count_quartet<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], T, lane, 0u, tacc);
+#endif
             if (lane == 0) { sh.meta[c][b].q = bad ? -1 - q : q; sh.meta[c][b].tips = t; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.full[c][b]);
