@@ -244,7 +244,7 @@ def run_ours(args):
     pin_map = torch.from_numpy(tmpmap.view(np.int32)).pin_memory()
     pin_q = torch.from_numpy(quartets.view(np.int32)).pin_memory()
     h_arr, h_map, h_q = pin_arr.numpy(), pin_map.numpy().view(np.uint32), pin_q.numpy().view(np.uint32)
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, args.steps)                     # the same K steps as the device-timed loop
     for _ in range(2):
         tetrad_b200.new_infer_resolved_quartets(h_arr, h_map, h_q, True, device=local)
     if world > 1:
