@@ -173,6 +173,9 @@ int64_t tq_format_tsv(const uint32_t *quartets, const uint32_t *rstat, const dou
                       char *out, int64_t cap);
 int     tq_round_scores(const double *rscor, int64_t n, double *out);
 int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, char *out, int64_t cap);
+/* the same lines for rows rows[0..n) of tips / weight (the shuffled order the wQMC input is written in, :308-327),
+ * without materialising the permuted arrays */
+int64_t tq_format_qmc_rows(const uint32_t *tips, const double *weight, const int64_t *rows, int64_t n, char *out, int64_t cap);
 int64_t tq_qmc_weights(const uint32_t *quartets, const uint32_t *rstat, const double *rscor, int64_t m, int weights,
                        int64_t min_snps, double min_ratio, uint32_t *tips_out, double *weight_out);
 

@@ -95,6 +95,8 @@ def _declare(lib):
     lib.tq_round_scores.argtypes = [vp, i64, vp]
     lib.tq_format_qmc.restype = i64
     lib.tq_format_qmc.argtypes = [vp, vp, i64, vp, i64]
+    lib.tq_format_qmc_rows.restype = i64
+    lib.tq_format_qmc_rows.argtypes = [vp, vp, vp, i64, vp, i64]
     lib.tq_qmc_weights.restype = i64
     lib.tq_qmc_weights.argtypes = [vp, vp, vp, i64, i32, i64, c.c_double, vp, vp]
     lib.tq_unrank.restype = i32
@@ -121,7 +123,7 @@ EXPORTS = [
     "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_set_option", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
     "tq_plan_destroy",
     "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
-    "tq_ctx_last_traffic", "tq_microbench", "tq_format_tsv", "tq_round_scores", "tq_format_qmc", "tq_qmc_weights",
+    "tq_ctx_last_traffic", "tq_microbench", "tq_format_tsv", "tq_round_scores", "tq_format_qmc", "tq_format_qmc_rows", "tq_qmc_weights",
 ]
 
 

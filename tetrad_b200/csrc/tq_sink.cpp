@@ -141,12 +141,13 @@ int64_t tq_qmc_weights(const uint32_t *quartets, const uint32_t *rstat, const do
     return n;
 }
 
-int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, char *out, int64_t cap)
+static int64_t format_qmc_rows(const uint32_t *tips, const double *weight, const int64_t *rows, int64_t n, char *out, int64_t cap)
 {
     if (n < 0 || (n > 0 && (!tips || !weight || !out))) return TQ_EINVAL;
     char *p = out;
-    for (int64_t i = 0; i < n; ++i) {
+    for (int64_t k = 0; k < n; ++k) {
         if (cap - (p - out) < 128) return TQ_ENOMEM;
+        const int64_t i = rows ? rows[k] : k;
         p = put_uint(p, tips[4 * i]); *p++ = ',';
         p = put_uint(p, tips[4 * i + 1]); *p++ = '|';
         p = put_uint(p, tips[4 * i + 2]); *p++ = ',';
@@ -157,6 +158,17 @@ int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, cha
         *p++ = '\n';
     }
     return (int64_t)(p - out);
+}
+
+int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, char *out, int64_t cap)
+{
+    return format_qmc_rows(tips, weight, nullptr, n, out, cap);
+}
+
+int64_t tq_format_qmc_rows(const uint32_t *tips, const double *weight, const int64_t *rows, int64_t n, char *out, int64_t cap)
+{
+    if (n > 0 && !rows) return TQ_EINVAL;
+    return format_qmc_rows(tips, weight, rows, n, out, cap);
 }
 
 }  // extern "C"

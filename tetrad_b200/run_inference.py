@@ -162,18 +162,28 @@ def qmc_weights(quartets, rstat, rscor, weights: int, min_snps: int = 0, min_rat
     return np.ascontiguousarray(tips[keep], dtype=np.uint32), np.ascontiguousarray(weight[keep], dtype=np.float64)
 
 
-def format_qmc_lines(tips: np.ndarray, weight: np.ndarray) -> bytes:
-    """``a,b|c,d:%.5f`` lines (run_inference.py:305), formatted in C (``tq_format_qmc``)."""
+def format_qmc_lines(tips: np.ndarray, weight: np.ndarray, rows=None) -> bytes:
+    """``a,b|c,d:%.5f`` lines (run_inference.py:305), formatted in C (``tq_format_qmc``); ``rows`` (an index
+    array, e.g. the shuffle of :308-327) selects and orders the lines without copying the arrays."""
     from . import _lib
     lib = _lib.load()
     tips = np.ascontiguousarray(tips, dtype=np.uint32).reshape(-1, 4)
     weight = np.ascontiguousarray(weight, dtype=np.float64)
     tp, wp = tips.ctypes.data, weight.ctypes.data
+    if rows is None:
+        def call(lo, hi, buf):
+            return lib.tq_format_qmc(tp + 16 * lo, wp + 8 * lo, hi - lo, buf, len(buf))
+        n = len(tips)
+    else:
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        if len(rows) and (rows.min() < 0 or rows.max() >= len(tips)):
+            raise IndexError("format_qmc_lines: row index out of range")
+        rp = rows.ctypes.data
 
-    def call(lo, hi, buf):
-        return lib.tq_format_qmc(tp + 16 * lo, wp + 8 * lo, hi - lo, buf, len(buf))
-
-    return b"".join(_format_parallel(call, len(tips), 128))
+        def call(lo, hi, buf):
+            return lib.tq_format_qmc_rows(tp, wp, rp + 8 * lo, hi - lo, buf, len(buf))
+        n = len(rows)
+    return b"".join(_format_parallel(call, n, 128))
 
 
 def read_quartets_tsv(path: Path):
@@ -221,7 +231,7 @@ def write_qmc_format(qrts_file: Path, qmc_in_file: Path, weights: int = 0, min_s
     tips, weight = qmc_weights(*results, weights, min_snps, min_ratio)
     perm = np.random.default_rng(rng).permutation(len(tips))
     with open(qmc_in_file, "wb") as out:
-        out.write(format_qmc_lines(tips[perm], weight[perm]))
+        out.write(format_qmc_lines(tips, weight, rows=perm))
     return len(tips)
 
 
@@ -326,8 +336,11 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
         rng = proj.bootstrap_rng.to_rng()
 
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=1) if overlap_sink else None
-    pending = None
+    # Two sink workers: the heavy part of a replicate's sink (TSV, wQMC input, wQMC itself) is independent of its
+    # neighbours', so two replicates' sinks run side by side; each waits for its predecessor before the ordered tail
+    # (tree files and the checkpoint), so replicates still become durable in order (reference :396-407).
+    pool = ThreadPoolExecutor(max_workers=2) if overlap_sink else None
+    pending = []
     exhaustive = proj.nqrts == proj.nqrts_total
     gpu_index = getattr(getattr(resolver, "device", None), "index", None)      # None for CPU stand-ins (tests)
     full = full_dev = None
@@ -392,9 +405,8 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
         if hasattr(resolver, "device"):
             torch.cuda.synchronize(resolver.device)
         t_gpu = time.perf_counter()
-        if pending is not None:
-            pending.result()                               # sinks finish (and checkpoint) in replicate order
-            pending = None
+        while len(pending) >= 2:
+            pending.pop(0).result()                        # at most two replicates' sinks in flight
         if rank == 0:
             rstat, rscor = out
             # D2H here (the GPU is idle anyway until the next launch); formatting, wQMC and the
@@ -403,26 +415,30 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
                 np.save(proj.workdir / f"{proj.name}.invariants_{idx}.npy",
                         invariants.cpu().numpy().view(np.uint32).reshape(-1, 16, 16))
             job = (idx, quartets, rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy(), rng_state)
-            pending = pool.submit(_sink_replicate, proj, *job) if pool is not None else _sink_replicate(proj, *job)
-            if pool is None:
-                pending = None
+            if pool is not None:
+                pending.append(pool.submit(_sink_replicate, proj, *job, after=pending[-1] if pending else None))
+            else:
+                _sink_replicate(proj, *job)
         logger.info(f"finished rep {idx}: {len(quartets)} quartets, prepare {t_prep - t_start:.3f} s, resolve "
                     f"{t_gpu - t_prep:.3f} s ({len(quartets) / max(t_gpu - t_prep, 1e-9):.3g} quartets/s), "
                     f"hand-off to sink {time.perf_counter() - t_gpu:.3f} s")
         proj.bootstrap_idx += 1
         proj.bootstrap_rng = rng_state
-    if pending is not None:
-        pending.result()
+    for fut in pending:
+        fut.result()
     if pool is not None:
         pool.shutdown()
 
 
-def _sink_replicate(proj: Project, idx: int, quartets, rstat, rscor, rng_state) -> None:
+def _sink_replicate(proj: Project, idx: int, quartets, rstat, rscor, rng_state, after=None) -> None:
     """Everything that happens to a replicate's results on the host: TSV, wQMC input, supertree,
-    tree files, and the JSON checkpoint that makes the replicate durable (reference :396-407)."""
+    tree files, and the JSON checkpoint that makes the replicate durable (reference :396-407).
+    ``after``: the future of the previous replicate's sink; the ordered tail waits for it."""
     snap = proj.model_copy(update=dict(bootstrap_idx=idx))
     write_quartets_tsv(snap.qrts_file, quartets, rstat, rscor)
     nwk = infer_supertree(snap, idx, proj.weights, rng=idx, results=(quartets, rstat, rscor))
+    if after is not None:
+        after.result()                                     # tree files and checkpoints in replicate order
     if nwk is not None:
         if idx == 0:
             proj.best_file.write_text(nwk + "\n")
