@@ -193,3 +193,34 @@ def test_qmc_weights_c_pass_equals_numpy_formulation(weights):
     tips2, wt2 = ri.qmc_weights(q2, r2, s2, weights, **kw)
     assert 0 < len(tips) < m and len(tips2) == len(tips)
     assert (tips == tips2).all() and wt.tobytes() == wt2.tobytes()
+
+
+def test_threaded_sink_equals_one_call(tmp_path):
+    """The sink formats ranges of 65 536 rows on a thread pool; the bytes must be those of one C call over all rows
+    (and of Python's own %-formatting on a sample), also for the shuffled wQMC lines addressed by an index array."""
+    import ctypes
+    from tetrad_b200 import _lib, run_inference as ri
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    m = 150_001
+    q = np.sort(rng.integers(0, 300, (m, 4)), axis=1).astype(np.uint32)
+    rstat = np.stack([rng.integers(0, 3, m), rng.integers(0, 90000, m)], axis=1).astype(np.uint32)
+    rscor = rng.random((m, 3)) * rng.choice([1e-4, 1.0, 5000.0], size=(m, 1))
+    ri.write_quartets_tsv(tmp_path / "a.tsv", q, rstat, rscor)
+    buf = ctypes.create_string_buffer(160 * m)
+    n = lib.tq_format_tsv(q.ctypes.data, rstat.ctypes.data, rscor.ctypes.data, m, buf, len(buf))
+    data = (tmp_path / "a.tsv").read_bytes()
+    assert n > 0 and data == buf.raw[:n]
+    lines = data.split(b"\n")
+    for i in (0, 65535, 65536, 131071, 131072, m - 1):
+        want = "%d\t%d\t%d\t%d\t%.6f\t%.6f\t%.6f\t%d\t%d" % (*q[i], *rscor[i], *rstat[i])
+        assert lines[i].decode() == want
+    tips, w = ri.qmc_weights(q, rstat, rscor, 1)
+    perm = rng.permutation(len(tips))
+    assert ri.format_qmc_lines(tips, w, rows=perm) == ri.format_qmc_lines(tips[perm], w[perm])
+    one = ctypes.create_string_buffer(128 * len(tips))
+    tp, wp = np.ascontiguousarray(tips[perm]), np.ascontiguousarray(w[perm])       # keep them alive across the call
+    k = lib.tq_format_qmc(tp.ctypes.data, wp.ctypes.data, len(tips), one, len(one))
+    assert ri.format_qmc_lines(tips, w, rows=perm) == one.raw[:k]
+    with pytest.raises(IndexError):
+        ri.format_qmc_lines(tips, w, rows=np.array([len(tips)]))
