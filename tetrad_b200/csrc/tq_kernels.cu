@@ -1557,6 +1557,9 @@ __device__ unsigned long long g_mma_clk[8];         // count: slot wait, stage 2
 #define TQ_MMA_SPLIT 0
 #endif
 
+#ifndef TQ_MMA_CPASYNC
+#define TQ_MMA_CPASYNC "cp.async.cg.shared.global"     // .cg bypasses L1; .ca (rows of consecutive quartets shared through L1) measured 3 % slower
+#endif
 #ifndef TQ_MMA_UNROLL
 #define TQ_MMA_UNROLL 1                       // unroll factor of the rank-chunk loop of stage 1
 #endif
@@ -1729,10 +1732,10 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
     const uint32_t pos0 = 0;
     auto issue = [&](uint32_t chunk) {
         const uint32_t s = ring_s + (chunk & (kMStages - 1)) * (4 * 32 * 16), off = chunk * kTileWords;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g0 + off) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 512), "l"(g1 + off) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1024), "l"(g2 + off) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1536), "l"(g3 + off) : "memory");
+        asm volatile(TQ_MMA_CPASYNC " [%0], [%1], 16;\n" ::"r"(s), "l"(g0 + off) : "memory");
+        asm volatile(TQ_MMA_CPASYNC " [%0], [%1], 16;\n" ::"r"(s + 512), "l"(g1 + off) : "memory");
+        asm volatile(TQ_MMA_CPASYNC " [%0], [%1], 16;\n" ::"r"(s + 1024), "l"(g2 + off) : "memory");
+        asm volatile(TQ_MMA_CPASYNC " [%0], [%1], 16;\n" ::"r"(s + 1536), "l"(g3 + off) : "memory");
     };
 #ifndef TQ_DBG_NO_LOAD
 #pragma unroll
