@@ -415,19 +415,23 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
     // (re)build the replicate state unless the caller presents the same arrays again
     const bool same = c->plan && c->key_arr == h_tmparr && c->key_loc == h_locus && c->key_ntips == ntips &&
                       c->key_ncols == ncols && c->key_epoch == epoch && epoch != 0;
+    // Host -> device copies that do not depend on the plan go first, so that they run while the host builds it.
+    if ((rc = grow(&c->d_quart, &c->cap_quart, (size_t)m * 16)) != TQ_OK) return rc;
+    TQ_CUDA(cudaMemcpyAsync(c->d_quart, h_quartets, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
+    c->last_h2d += m * 16;
     if (!same) {
         c->key_arr = c->key_loc = nullptr;          // nothing is cached until the rebuild below has succeeded
-        if (c->plan) { tq_plan_destroy(c->plan); c->plan = nullptr; }
-        if ((rc = tq_plan_create(h_locus, ncols, locus_stride, c->device, c->stream, &c->plan)) != TQ_OK) return rc;
-        c->last_h2d += (int64_t)((2 * c->plan->ntiles + 1 + 3 * c->plan->ntiles * tq::kTileLoci) * 4);
         const size_t arr_bytes = (size_t)ntips * (size_t)ncols;
         if ((rc = grow(&c->d_tmparr, &c->cap_tmparr, arr_bytes + 16)) != TQ_OK) return rc;
-        if ((rc = grow(&c->d_planes, &c->cap_planes, (size_t)ntips * (size_t)c->plan->row_u4 * 16 + 16)) != TQ_OK) return rc;
         if (arr_bytes) {
             TQ_CUDA(cudaMemcpy2DAsync(c->d_tmparr, (size_t)ncols, h_tmparr, (size_t)row_stride, (size_t)ncols,
                                       (size_t)ntips, cudaMemcpyHostToDevice, c->stream));
             c->last_h2d += (int64_t)arr_bytes;
         }
+        if (c->plan) { tq_plan_destroy(c->plan); c->plan = nullptr; }
+        if ((rc = tq_plan_create(h_locus, ncols, locus_stride, c->device, c->stream, &c->plan)) != TQ_OK) return rc;
+        c->last_h2d += (int64_t)((2 * c->plan->ntiles + 1 + 3 * c->plan->ntiles * tq::kTileLoci) * 4);
+        if ((rc = grow(&c->d_planes, &c->cap_planes, (size_t)ntips * (size_t)c->plan->row_u4 * 16 + 16)) != TQ_OK) return rc;
         if ((rc = tq_pack(c->plan, (const uint8_t *)c->d_tmparr, ntips, ncols, (uint32_t *)c->d_planes, c->stream)) != TQ_OK)
             return rc;
         c->key_arr = h_tmparr; c->key_loc = h_locus; c->key_ntips = ntips; c->key_ncols = ncols;
@@ -438,11 +442,8 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
     const size_t o_scor = 0, o_stat = o_scor + (size_t)m * 24, o_mr = o_stat + (size_t)m * 8,
                  o_status = o_mr + (((size_t)m * 4 + 15) & ~(size_t)15),
                  o_counts = o_status + 16, out_bytes = o_counts + (h_counts ? (size_t)m * 1024 : 0);
-    if ((rc = grow(&c->d_quart, &c->cap_quart, (size_t)m * 16)) != TQ_OK) return rc;
     if ((rc = grow(&c->d_out, &c->cap_out, out_bytes)) != TQ_OK) return rc;
     char *o = static_cast<char *>(c->d_out);
-    TQ_CUDA(cudaMemcpyAsync(c->d_quart, h_quartets, (size_t)m * 16, cudaMemcpyHostToDevice, c->stream));
-    c->last_h2d += m * 16;
     TQ_CUDA(cudaMemsetAsync(o + o_status, 0, 16, c->stream));
     if ((rc = tq_resolve(c->plan, (const uint32_t *)c->d_planes, ntips, (const uint32_t *)c->d_quart, m, subsample,
                          seed, (double *)(o + o_scor), (uint32_t *)(o + o_stat),
