@@ -77,10 +77,10 @@ def new_infer_resolved_quartets(tmparr: np.ndarray, tmpmap: np.ndarray, quartets
     quartets_in = quartets
     quartets = np.ascontiguousarray(quartets, dtype=np.uint32).reshape(-1, 4)
     m = quartets.shape[0]
-    rscor = np.zeros((m, 3), dtype=np.float64)
-    rstat = np.zeros((m, 2), dtype=np.uint32)
-    counts = np.zeros((m, 16, 16), dtype=np.uint32) if return_counts else None
-    minrank = np.zeros(m, dtype=np.uint32) if return_counts else None
+    rscor = np.empty((m, 3), dtype=np.float64)          # every element is written by the call (or it raises)
+    rstat = np.empty((m, 2), dtype=np.uint32)
+    counts = np.empty((m, 16, 16), dtype=np.uint32) if return_counts else None
+    minrank = np.empty(m, dtype=np.uint32) if return_counts else None
     _lib.check(lib.tq_resolve_host(
         _ctx(device), tmparr.ctypes.data, ntips, ncols, tmparr.strides[0],
         locus_ptr, locus_stride, quartets.ctypes.data, m, int(bool(subsample_snps)),
