@@ -86,6 +86,10 @@ int  tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k,
  */
 int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t row_stride,
             uint32_t *d_planes, void *stream);
+/* Only tip rows [tip_lo, tip_hi) of the same matrices (d_tmparr and d_planes are the bases of the full matrices):
+ * under one process per GPU every rank packs its share of the rows and the planes are all-gathered. */
+int tq_pack_rows(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t row_stride,
+                 int64_t tip_lo, int64_t tip_hi, uint32_t *d_planes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Quartet unranking on the device.  Replaces _index_to_combination / iter_chunks_full
@@ -113,6 +117,11 @@ int tq_unrank(int device, const int64_t *d_ranks, int64_t start, int64_t m, int6
 int tq_boot_pack(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
                  const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
                  uint32_t *d_srccol, uint32_t *d_planes, void *stream);
+/* The same replicate, planes of tip rows [tip_lo, tip_hi) only (the column orders in d_srccol are built in full by
+ * every caller; coins are keyed by the global tip index, so the rows equal those of the unsharded call bit for bit). */
+int tq_boot_pack_rows(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
+                      int64_t tip_lo, int64_t tip_hi, const uint32_t *d_src_start, uint32_t seed_shuffle,
+                      uint32_t seed_ambig, uint32_t *d_srccol, uint32_t *d_planes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3+K4: resolve.  For each of the m quartets in d_quartets u32[m][4]:

@@ -30,16 +30,53 @@ def mats_from_mats0(m0):
                      t.transpose(0, 1, 4, 2, 3).reshape(-1, 16, 16)], axis=1)
 
 
-def assert_scores_close(got, want, nsnps, rel=1e-6):
-    """north_star tolerance: 1e-6 relative per split.  Scores that are exact zeros in exact
-    arithmetic (rank-deficient flattenings) come out of any SVD as rounding noise of size
-    ~eps*sigma_max <= eps*nsnps, so differences below 1e-9*max(1,nsnps) are also accepted."""
+EPS = float(np.finfo(np.float64).eps)
+PARITY_LOG = {}          # test label -> worst errors seen (written to gpurun_out/ at session end)
+
+
+def assert_scores_close(got, want, nsnps, rel=1e-6, counts=None, label=None):
+    """north_star tolerance: 1e-6 relative per split.  Every singular value any backward-stable SVD returns
+    carries an absolute error of a few eps * sigma_max, so a score that is an exact zero in exact arithmetic
+    (rank-deficient flattenings) comes out of LAPACK as noise of that size while the Jacobi returns 0: differences
+    below 64 * eps * sigma_max are accepted as well.  sigma_max <= ||T||_F, taken from the counts when the caller
+    has them and bounded by nsnps (non-negative integers that sum to nsnps) otherwise.  Returns the worst relative
+    error among scores above the floor and the worst absolute error in units of eps * ||T||_F; both are logged
+    under `label`."""
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
-    floor = 1e-9 * np.maximum(1.0, np.asarray(nsnps, dtype=np.float64))[:, None]
+    if counts is not None:
+        fro = np.sqrt((np.asarray(counts, dtype=np.float64).reshape(len(got), -1) ** 2).sum(1))
+    else:
+        fro = np.asarray(nsnps, dtype=np.float64)
+    fro = np.maximum(fro, 1.0)[:, None]
+    floor = 64.0 * EPS * fro
     err = np.abs(got - want)
-    ok = (err <= rel * np.maximum(np.abs(got), np.abs(want))) | (err <= floor)
-    assert ok.all(), f"score mismatch: worst abs err {err[~ok].max()} at {np.argwhere(~ok)[:5]}"
+    mag = np.maximum(np.abs(got), np.abs(want))
+    ok = (err <= rel * mag) | (err <= floor)
+    above = mag > floor
+    worst_rel = float((err[above] / mag[above]).max()) if above.any() else 0.0
+    worst_abs = float((err / (EPS * fro)).max()) if err.size else 0.0
+    label = label or os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0].split("::")[-1]
+    if label:
+        cur = PARITY_LOG.setdefault(label, dict(n=0, worst_rel=0.0, worst_abs_in_eps_fro=0.0))
+        cur["n"] += int(got.shape[0])
+        cur["worst_rel"] = max(cur["worst_rel"], worst_rel)
+        cur["worst_abs_in_eps_fro"] = max(cur["worst_abs_in_eps_fro"], worst_abs)
+    assert ok.all(), f"score mismatch: worst abs err {err[~ok].max()} (rel {worst_rel:.3g}) at {np.argwhere(~ok)[:5]}"
+    return worst_rel, worst_abs
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Observed score errors of this session -> gpurun_out/parity_errors.json (copied to profiles/ per round)."""
+    if not PARITY_LOG:
+        return
+    import json
+    out = ROOT / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        (out / "parity_errors.json").write_text(json.dumps(PARITY_LOG, indent=1, sort_keys=True) + "\n")
+    except OSError:
+        pass
 
 
 def assert_best_matches(best, rscor_ref, rstat_ref):

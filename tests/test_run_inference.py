@@ -224,3 +224,27 @@ def test_threaded_sink_equals_one_call(tmp_path):
     assert ri.format_qmc_lines(tips, w, rows=perm) == one.raw[:k]
     with pytest.raises(IndexError):
         ri.format_qmc_lines(tips, w, rows=np.array([len(tips)]))
+
+
+def test_sink_formats_non_scores_without_overrunning(tmp_path):
+    """Values the kernel never produces (inf, NaN, negative, 1e300) are written as printf would write them, through a
+    bounded temporary: the row budget is checked, nothing is written past it, and a short buffer is an error with a
+    message (the advance used to be snprintf's would-be length)."""
+    import ctypes
+    from tetrad_b200 import _lib, run_inference as ri
+    lib = _lib.load()
+    q = np.array([[0, 1, 2, 3], [4, 5, 6, 7], [1, 2, 3, 4]], dtype=np.uint32)
+    rstat = np.array([[0, 10], [1, 20], [2, 30]], dtype=np.uint32)
+    rscor = np.array([[1e300, 2.5, -1.0], [np.inf, np.nan, 3.0], [0.125, 0.25, 0.5]])
+    ri.write_quartets_tsv(tmp_path / "odd.tsv", q, rstat, rscor)
+    lines = (tmp_path / "odd.tsv").read_text().split("\n")
+    assert lines[0] == "0\t1\t2\t3\t%.6f\t2.500000\t-1.000000\t0\t10" % 1e300
+    assert lines[1] == "4\t5\t6\t7\tinf\tnan\t3.000000\t1\t20"
+    assert lines[2] == "1\t2\t3\t4\t0.125000\t0.250000\t0.500000\t2\t30"
+    small = ctypes.create_string_buffer(3 * 160)
+    n = lib.tq_format_tsv(q.ctypes.data, rstat.ctypes.data, rscor.ctypes.data, 3, small, len(small))
+    assert n == _lib.TQ_ENOMEM and b"buffer too small" in lib.tq_last_error()
+    tips = np.ascontiguousarray(q)
+    w = np.array([1e300, 1.5, np.inf])
+    text = ri.format_qmc_lines(tips, w).decode().split("\n")
+    assert text[0] == "0,1|2,3:%.5f" % 1e300 and text[1] == "4,5|6,7:1.50000" and text[2] == "1,2|3,4:inf"

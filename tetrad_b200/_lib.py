@@ -14,14 +14,19 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 _ROOT = _PKG.parent
 LIB_PATH = _PKG / "libtetrad_b200.so"
-SOURCES = [_PKG / "csrc" / "tq_kernels.cu", _PKG / "csrc" / "tq_api.cu", _PKG / "csrc" / "tq_sink.cpp"]
-HEADERS = [_PKG / "csrc" / "tq_kernels.cuh", _ROOT / "include" / "tetrad_b200.h"]
+CSRC = _PKG / "csrc"
+SOURCES = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
+HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [_ROOT / "include" / "tetrad_b200.h"]
+BUILD_DIR = _PKG / "build"
 
-NVCC_FLAGS = [
+# sm_100a only (no PTX for other architectures, no multi-arch fat binary); -lineinfo so that ncu's source page maps to
+# these files
+NVCC_COMPILE = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
-    "-Xlinker", "-rpath,/usr/local/cuda/lib64",
+    "-Xcompiler", "-fPIC", "-cudart", "shared",
 ]
+NVCC_LINK = ["-shared", "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+NVCC_FLAGS = NVCC_COMPILE + NVCC_LINK
 
 TQ_OK, TQ_EINVAL, TQ_ELOCUS, TQ_ECUDA, TQ_ENOMEM = 0, -1, -2, -3, -4
 
@@ -50,20 +55,41 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > built for p in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the CUDA sources for sm_100a into ``tetrad_b200/libtetrad_b200.so``."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None) -> Path:
+    """Compile the CUDA sources for sm_100a into ``tetrad_b200/libtetrad_b200.so``: one ``nvcc -c`` per translation
+    unit (in parallel, objects under ``tetrad_b200/build/``; a unit is recompiled when it or any header is newer
+    than its object), then one link.  ``defines`` (e.g. ``["TQ_MMA_TIMERS"]``) and ``out`` build a variant library for
+    measurements."""
+    from concurrent.futures import ThreadPoolExecutor
+    target = Path(out) if out else LIB_PATH
+    if not force and not defines and out is None and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, SOURCES)]
+    objdir = BUILD_DIR / ("default" if not defines else "_".join(d.replace("=", "-") for d in defines))
+    objdir.mkdir(parents=True, exist_ok=True)
+    newest_header = max(p.stat().st_mtime for p in HEADERS)
+    nvcc = _nvcc()
+
+    def compile_one(src: Path):
+        obj = objdir / (src.name + ".o")
+        if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, newest_header):
+            return obj, ""
+        cmd = [nvcc, *NVCC_COMPILE, *[f"-D{d}" for d in defines], "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name} ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
+        return obj, proc.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as pool:
+        results = list(pool.map(compile_one, SOURCES))
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    proc = subprocess.run(cmd, capture_output=True, text=True)
+        print("\n".join(err for _, err in results if err))
+    proc = subprocess.run([nvcc, *NVCC_LINK, "-o", str(target), *[str(o) for o, _ in results]],
+                          capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
-    if verbose:
-        print(proc.stderr)
-    return LIB_PATH
+        raise RuntimeError(f"link failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
+    return target
 
 
 def _declare(lib):
@@ -105,6 +131,10 @@ def _declare(lib):
     lib.tq_boot_pack.argtypes = [vp, vp, i64, i64, vp, c.c_uint32, c.c_uint32, vp, vp, vp]
     lib.tq_pack.restype = i32
     lib.tq_pack.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.tq_pack_rows.restype = i32
+    lib.tq_pack_rows.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp]
+    lib.tq_boot_pack_rows.restype = i32
+    lib.tq_boot_pack_rows.argtypes = [vp, vp, i64, i64, i64, i64, vp, c.c_uint32, c.c_uint32, vp, vp, vp]
     lib.tq_resolve.restype = i32
     lib.tq_resolve.argtypes = [vp, vp, i64, vp, i64, i32, u64, vp, vp, vp, vp, vp, vp]
     lib.tq_ctx_create.restype = i32
@@ -122,7 +152,7 @@ def _declare(lib):
 EXPORTS = [
     "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_set_option", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
     "tq_plan_destroy",
-    "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
+    "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_pack_rows", "tq_boot_pack_rows", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
     "tq_ctx_last_traffic", "tq_microbench", "tq_format_tsv", "tq_round_scores", "tq_format_qmc", "tq_format_qmc_rows", "tq_qmc_weights",
 ]
 

@@ -77,9 +77,15 @@ def device_quartets(nsamples: int, device: int = 0, ranks=None, start: int = 0, 
     dev = torch.device("cuda", device)
     stream = torch.cuda.current_stream(dev).cuda_stream
     if ranks is not None:
-        r = ranks if isinstance(ranks, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ranks, dtype=np.int64))
-        r = r.to(dev, dtype=torch.int64).contiguous()
-        if r.numel() and (int(r.min()) < 0 or int(r.max()) >= comb(nsamples, 4)):
+        if isinstance(ranks, torch.Tensor):
+            r = ranks.to(dev, dtype=torch.int64).contiguous()
+            bad = bool(r.numel()) and (int(r.min()) < 0 or int(r.max()) >= comb(nsamples, 4))    # device tensor: one sync
+        else:
+            host = np.ascontiguousarray(ranks, dtype=np.int64)
+            bad = bool(host.size) and (int(host.min()) < 0 or int(host.max()) >= comb(nsamples, 4))   # checked on the host
+            from .resolve_quartets import upload
+            r = upload(host, dev)
+        if bad:
             raise ValueError("quartet rank out of range")
         out = torch.empty((r.numel(), 4), dtype=torch.int32, device=dev)
         _lib.check(lib.tq_unrank(device, r.data_ptr(), 0, r.numel(), nsamples, out.data_ptr(), stream))

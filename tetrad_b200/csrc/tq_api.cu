@@ -2,11 +2,13 @@
 // host-buffer convenience entry, micro-benchmarks.  Host code only; kernels are in tq_kernels.cu.
 #include "../../include/tetrad_b200.h"
 #include "tq_kernels.cuh"
+#include "tq_error.h"
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <unordered_set>
 #include <vector>
@@ -15,14 +17,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 
-int fail(int code, const char *fmt, ...)
-{
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
+#define fail tq::set_error
 
 #define TQ_CUDA(expr)                                                                      \
     do {                                                                                   \
@@ -40,14 +35,70 @@ struct DeviceGuard {
 
 }  // namespace
 
+int tq::set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// Pinned host buffers for the plan tables.  A replicate loop creates one plan per replicate while the previous
+// replicate's kernels are still running: the upload must neither block the host (pageable memory would, once the
+// driver's staging buffers are full behind a 40 ms kernel) nor pay cudaHostAlloc every time.  Buffers go back to a
+// free list together with the event that marks the end of their last upload.
+namespace {
+struct PinnedBuf { uint32_t *ptr = nullptr; size_t words = 0; cudaEvent_t done = nullptr; };
+std::mutex g_pinned_mu;
+std::vector<PinnedBuf> g_pinned_free;
+
+PinnedBuf pinned_get(size_t words)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        for (size_t i = 0; i < g_pinned_free.size(); ++i)
+            if (g_pinned_free[i].words >= words && g_pinned_free[i].words <= 2 * words + 4096) {
+                PinnedBuf b = g_pinned_free[i];
+                g_pinned_free.erase(g_pinned_free.begin() + (long)i);
+                if (b.done) cudaEventSynchronize(b.done);          // its last upload (long over in practice)
+                return b;
+            }
+    }
+    PinnedBuf b;
+    const size_t want = words + words / 8 + 1024;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&b.ptr), want * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return PinnedBuf{};
+    }
+    b.words = want;
+    cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming);
+    return b;
+}
+
+void pinned_put(PinnedBuf b)
+{
+    if (!b.ptr) return;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    if (g_pinned_free.size() >= 8) {                       // keep a handful; the rest goes back to the driver
+        if (b.done) { cudaEventSynchronize(b.done); cudaEventDestroy(b.done); }
+        cudaFreeHost(b.ptr);
+        return;
+    }
+    g_pinned_free.push_back(b);
+}
+}  // namespace
+
 struct tq_plan {
     int device = 0;
     int num_sms = 0;
     int64_t ncols = 0, nloci = 0, ntiles = 0, row_u4 = 0, max_len = 0, padded_cols = 0;
     void *d_tables = nullptr;      // one allocation: tile_off | tile_k | loc_start | loc_len
     cudaStream_t stream = nullptr; // the tables are stream-ordered memory of the stream the plan was created on
-    std::vector<uint32_t> h_tables; // host copy of the same tables
-    size_t o_off = 0, o_k = 0, o_start = 0, o_len = 0, o_run = 0;
+    std::vector<uint32_t> h_vec;    // host copy of the same tables: a vector for host-only plans,
+    PinnedBuf h_pin;                // a pinned buffer (the upload's source) for device plans
+    const uint32_t *h_tables() const { return h_pin.ptr ? h_pin.ptr : h_vec.data(); }
+    size_t o_off = 0, o_k = 0, o_start = 0, o_len = 0, o_run = 0, o_pos = 0;
     tq::PlanDev dev{};
 };
 
@@ -122,11 +173,21 @@ static int build_plan(const std::vector<uint32_t> &run_start, const std::vector<
     for (size_t i = 1; i < bucket.size(); ++i) bucket[i] += bucket[i - 1];
     const int64_t ntiles = (nloci + tq::kTileLoci - 1) / tq::kTileLoci;
     const int64_t lpad = ntiles * tq::kTileLoci;
-    std::vector<uint32_t> tables;
-    // layout: tile_off[ntiles+1] | tile_k[ntiles] | loc_start[lpad] | loc_len[lpad] | loc_run[lpad]
+    std::vector<uint32_t> vec;
+    PinnedBuf pin;
+    // layout: tile_off[ntiles+1] | tile_k[ntiles] | loc_start[lpad] | loc_len[lpad] | loc_run[lpad] | loc_pos[lpad+1]
     const size_t o_off = 0, o_k = (size_t)ntiles + 1, o_start = o_k + (size_t)ntiles,
-                 o_len = o_start + (size_t)lpad, o_run = o_len + (size_t)lpad, total = o_run + (size_t)lpad;
-    tables.assign(total + 4, 0u);
+                 o_len = o_start + (size_t)lpad, o_run = o_len + (size_t)lpad, o_pos = o_run + (size_t)lpad,
+                 total = o_pos + (size_t)lpad + 1;
+    if (device >= 0) {
+        DeviceGuard guard(device);
+        pin = pinned_get(total + 4);
+        if (!pin.ptr) return fail(TQ_ENOMEM, "tq_plan_create: no pinned host memory for the plan tables");
+        memset(pin.ptr, 0, (total + 4) * sizeof(uint32_t));
+    } else {
+        vec.assign(total + 4, 0u);
+    }
+    uint32_t *tables = pin.ptr ? pin.ptr : vec.data();
     for (int64_t r = 0; r < nloci; ++r) {
         const int64_t pos = bucket[max_len - run_len[r]]++;
         tables[o_start + pos] = run_start[r];
@@ -140,23 +201,31 @@ static int build_plan(const std::vector<uint32_t> &run_start, const std::vector<
         tables[o_k + t] = k;
         off += (int64_t)k * tq::kTileWords;
         padded += (int64_t)k * tq::kTileLoci;
-        if (off >= ((int64_t)1 << 31)) return fail(TQ_EINVAL, "tq_plan_create: packed row too large");
+        if (off >= ((int64_t)1 << 31)) { pinned_put(pin); return fail(TQ_EINVAL, "tq_plan_create: packed row too large"); }
     }
     tables[o_off + ntiles] = (uint32_t)off;
+    {   // columns of the sorted loci before l: where locus l's columns sit once all columns are grouped by sorted locus
+        uint32_t pos = 0;
+        for (int64_t l = 0; l < lpad; ++l) { tables[o_pos + l] = pos; pos += tables[o_len + l]; }
+        tables[o_pos + lpad] = pos;
+    }
 
     tq_plan *p = new (std::nothrow) tq_plan();
-    if (!p) return fail(TQ_ENOMEM, "tq_plan_create: out of host memory");
+    if (!p) { pinned_put(pin); return fail(TQ_ENOMEM, "tq_plan_create: out of host memory"); }
     p->device = device;
     p->ncols = ncols; p->nloci = nloci; p->ntiles = ntiles; p->row_u4 = off;
     p->max_len = max_len; p->padded_cols = padded;
-    p->o_off = o_off; p->o_k = o_k; p->o_start = o_start; p->o_len = o_len; p->o_run = o_run;
+    p->o_off = o_off; p->o_k = o_k; p->o_start = o_start; p->o_len = o_len; p->o_run = o_run; p->o_pos = o_pos;
     p->dev.ntiles = (int)ntiles;
     p->dev.row_u4 = (uint32_t)off;
+    p->dev.ncols = (uint32_t)ncols;
+    p->dev.nloci = (uint32_t)nloci;
     if (device < 0) {               // host-only plan: layout queries, no kernels
-        p->h_tables.swap(tables);
+        p->h_vec.swap(vec);
         *out = p;
         return TQ_OK;
     }
+    p->h_pin = pin;
 
     DeviceGuard guard(device);
     cudaError_t e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -165,12 +234,12 @@ static int build_plan(const std::vector<uint32_t> &run_start, const std::vector<
     if (e == cudaSuccess) e = keep_pool_cached(device);
     p->stream = (cudaStream_t)stream;
     if (e == cudaSuccess) e = cudaMallocAsync(&p->d_tables, (total + 4) * sizeof(uint32_t), p->stream);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(p->d_tables, tables.data(), (total + 4) * sizeof(uint32_t),
-                            cudaMemcpyHostToDevice, (cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);   // `tables` is pageable
+    if (e == cudaSuccess)       // pinned source owned by the plan: asynchronous, the host goes on
+        e = cudaMemcpyAsync(p->d_tables, tables, (total + 4) * sizeof(uint32_t), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaEventRecord(p->h_pin.done, (cudaStream_t)stream);
     if (e != cudaSuccess) {
         if (p->d_tables) cudaFreeAsync(p->d_tables, p->stream);
+        pinned_put(p->h_pin);
         delete p;
         return fail(TQ_ECUDA, "tq_plan_create: %s", cudaGetErrorString(e));
     }
@@ -180,7 +249,7 @@ static int build_plan(const std::vector<uint32_t> &run_start, const std::vector<
     p->dev.loc_start = base + o_start;
     p->dev.loc_len = base + o_len;
     p->dev.loc_run = base + o_run;
-    p->h_tables.swap(tables);
+    p->dev.loc_pos = base + o_pos;
     *out = p;
     return TQ_OK;
 }
@@ -243,7 +312,7 @@ int tq_plan_tables(const tq_plan *plan, uint32_t *tile_off, uint32_t *tile_k, ui
                    uint32_t *loc_len, uint32_t *loc_run)
 {
     if (!plan) return fail(TQ_EINVAL, "tq_plan_tables: plan is NULL");
-    const uint32_t *t = plan->h_tables.data();
+    const uint32_t *t = plan->h_tables();
     const size_t nt = (size_t)plan->ntiles, lp = nt * tq::kTileLoci;
     if (tile_off) memcpy(tile_off, t + plan->o_off, (nt + 1) * sizeof(uint32_t));
     if (tile_k) memcpy(tile_k, t + plan->o_k, nt * sizeof(uint32_t));
@@ -260,6 +329,7 @@ void tq_plan_destroy(tq_plan *plan)
         DeviceGuard guard(plan->device);
         cudaFreeAsync(plan->d_tables, plan->stream);
     }
+    pinned_put(plan->h_pin);
     delete plan;
 }
 
@@ -275,19 +345,27 @@ int tq_plan_info(const tq_plan *plan, int64_t info[8])
 // ------------------------------------------------------------------------------------------
 // device-buffer entries
 // ------------------------------------------------------------------------------------------
-int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t row_stride,
-            uint32_t *d_planes, void *stream)
+int tq_pack_rows(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t row_stride,
+                 int64_t tip_lo, int64_t tip_hi, uint32_t *d_planes, void *stream)
 {
     if (!plan) return fail(TQ_EINVAL, "tq_pack: plan is NULL");
     if (plan->device < 0) return fail(TQ_EINVAL, "tq_pack: host-only plan (device < 0)");
     if (ntips < 0 || ntips > 65535) return fail(TQ_EINVAL, "tq_pack: ntips=%lld out of range", (long long)ntips);
-    if (ntips == 0 || plan->row_u4 == 0) return TQ_OK;
+    if (tip_lo < 0 || tip_hi < tip_lo || tip_hi > ntips)
+        return fail(TQ_EINVAL, "tq_pack: tip rows [%lld, %lld) outside [0, %lld)", (long long)tip_lo, (long long)tip_hi, (long long)ntips);
+    if (tip_hi == tip_lo || plan->row_u4 == 0) return TQ_OK;
     if (!d_tmparr || !d_planes) return fail(TQ_EINVAL, "tq_pack: NULL device pointer");
     if (row_stride < plan->ncols) return fail(TQ_EINVAL, "tq_pack: row_stride < ncols");
     if (((uintptr_t)d_planes & 15u) != 0) return fail(TQ_EINVAL, "tq_pack: d_planes must be 16-byte aligned");
     DeviceGuard guard(plan->device);
-    TQ_CUDA(tq::launch_pack(plan->dev, d_tmparr, ntips, row_stride, d_planes, (cudaStream_t)stream));
+    TQ_CUDA(tq::launch_pack(plan->dev, d_tmparr, tip_lo, tip_hi, row_stride, d_planes, (cudaStream_t)stream));
     return TQ_OK;
+}
+
+int tq_pack(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, int64_t row_stride,
+            uint32_t *d_planes, void *stream)
+{
+    return tq_pack_rows(plan, d_tmparr, ntips, row_stride, 0, ntips, d_planes, stream);
 }
 
 int tq_unrank(int device, const int64_t *d_ranks, int64_t start, int64_t m, int64_t ntips, uint32_t *d_quartets,
@@ -304,20 +382,30 @@ int tq_unrank(int device, const int64_t *d_ranks, int64_t start, int64_t m, int6
     return TQ_OK;
 }
 
-int tq_boot_pack(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
-                 const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
-                 uint32_t *d_srccol, uint32_t *d_planes, void *stream)
+int tq_boot_pack_rows(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
+                      int64_t tip_lo, int64_t tip_hi, const uint32_t *d_src_start, uint32_t seed_shuffle,
+                      uint32_t seed_ambig, uint32_t *d_srccol, uint32_t *d_planes, void *stream)
 {
     if (!plan) return fail(TQ_EINVAL, "tq_boot_pack: plan is NULL");
     if (plan->device < 0) return fail(TQ_EINVAL, "tq_boot_pack: host-only plan (device < 0)");
     if (ntips < 0 || ntips > 65535) return fail(TQ_EINVAL, "tq_boot_pack: ntips=%lld out of range", (long long)ntips);
+    if (tip_lo < 0 || tip_hi < tip_lo || tip_hi > ntips)
+        return fail(TQ_EINVAL, "tq_boot_pack: tip rows [%lld, %lld) outside [0, %lld)", (long long)tip_lo, (long long)tip_hi, (long long)ntips);
     if (ntips == 0 || plan->row_u4 == 0) return TQ_OK;
     if (!d_seqarr || !d_src_start || !d_srccol || !d_planes) return fail(TQ_EINVAL, "tq_boot_pack: NULL device pointer");
     if (((uintptr_t)d_planes & 15u) != 0) return fail(TQ_EINVAL, "tq_boot_pack: d_planes must be 16-byte aligned");
     DeviceGuard guard(plan->device);
-    TQ_CUDA(tq::launch_boot_pack(plan->dev, d_seqarr, ntips, row_stride, d_src_start, seed_shuffle, seed_ambig,
+    TQ_CUDA(tq::launch_boot_pack(plan->dev, d_seqarr, tip_lo, tip_hi, row_stride, d_src_start, seed_shuffle, seed_ambig,
                                  d_srccol, d_planes, (cudaStream_t)stream));
     return TQ_OK;
+}
+
+int tq_boot_pack(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
+                 const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
+                 uint32_t *d_srccol, uint32_t *d_planes, void *stream)
+{
+    return tq_boot_pack_rows(plan, d_seqarr, ntips, row_stride, 0, ntips, d_src_start, seed_shuffle, seed_ambig,
+                             d_srccol, d_planes, stream);
 }
 
 int tq_resolve(const tq_plan *plan, const uint32_t *d_planes, int64_t ntips,
@@ -430,7 +518,7 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
         }
         if (c->plan) { tq_plan_destroy(c->plan); c->plan = nullptr; }
         if ((rc = tq_plan_create(h_locus, ncols, locus_stride, c->device, c->stream, &c->plan)) != TQ_OK) return rc;
-        c->last_h2d += (int64_t)((2 * c->plan->ntiles + 1 + 3 * c->plan->ntiles * tq::kTileLoci) * 4);
+        c->last_h2d += (int64_t)((2 * c->plan->ntiles + 2 + 4 * c->plan->ntiles * tq::kTileLoci) * 4);
         if ((rc = grow(&c->d_planes, &c->cap_planes, (size_t)ntips * (size_t)c->plan->row_u4 * 16 + 16)) != TQ_OK) return rc;
         if ((rc = tq_pack(c->plan, (const uint8_t *)c->d_tmparr, ntips, ncols, (uint32_t *)c->d_planes, c->stream)) != TQ_OK)
             return rc;

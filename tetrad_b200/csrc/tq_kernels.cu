@@ -97,213 +97,6 @@ static constexpr double kEps = 2.220446049250313e-16;
 static constexpr int kMaxSweeps = 30;
 
 // ------------------------------------------------------------------------------------------
-// K1: pack
-// grid (ntiles, ntips), 128 threads.  warp w packs ranks w, w+4, ...; lane = word (32 loci).
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pack_kernel(PlanDev plan, const uint8_t *__restrict__ tmparr,
-                                                   int64_t row_stride, uint4 *__restrict__ planes)
-{
-    const int tile = blockIdx.x;
-    const int tip = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const uint32_t K = plan.tile_k[tile];
-    const uint32_t off = plan.tile_off[tile];
-    const uint8_t *row = tmparr + (int64_t)tip * row_stride;
-    uint4 *out = planes + (size_t)tip * plan.row_u4 + off;
-    const uint32_t l0 = (uint32_t)tile * kTileLoci + lane * 32;
-    for (uint32_t k = warp; k < K; k += 4) {
-        uint4 w = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 4
-        for (int b = 0; b < 32; ++b) {
-            const uint32_t len = __ldg(plan.loc_len + l0 + b);
-            if (k < len) {
-                const uint32_t code = row[(size_t)__ldg(plan.loc_start + l0 + b) + k];
-                const uint32_t bit = 1u << b;
-                w.x |= (code == 0u) ? bit : 0u;
-                w.y |= (code == 1u) ? bit : 0u;
-                w.z |= (code == 2u) ? bit : 0u;
-                w.w |= (code == 3u) ? bit : 0u;
-            }
-        }
-        out[k * kTileWords + lane] = w;
-    }
-}
-
-cudaError_t launch_pack(const PlanDev &plan, const uint8_t *d_tmparr, int64_t ntips,
-                        int64_t row_stride, uint32_t *d_planes, cudaStream_t stream)
-{
-    if (plan.ntiles == 0 || ntips == 0) return cudaSuccess;
-    dim3 grid((unsigned)plan.ntiles, (unsigned)ntips);
-    pack_kernel<<<grid, 128, 0, stream>>>(plan, d_tmparr, row_stride,
-                                          reinterpret_cast<uint4 *>(d_planes));
-    ++g_launches;
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
-// Quartet unranking (reference tetrad/src/combinations.py:94-106, _index_to_combination):
-// lexicographic rank in itertools.combinations(range(n), 4) -> (a, b, c, d).  The number of
-// quartets whose first id is < a is C(n,4) - C(n-a,4), and so on down the levels; each level is
-// a binary search on a closed-form binomial (C(n,4) < 2^32 is asserted by the reference).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t choose2(uint64_t m) { return m < 2 ? 0 : m * (m - 1) / 2; }
-__device__ __forceinline__ uint64_t choose3(uint64_t m) { return m < 3 ? 0 : m * (m - 1) / 2 * (m - 2) / 3; }
-__device__ __forceinline__ uint64_t choose4(uint64_t m) { return m < 4 ? 0 : m * (m - 1) / 2 * (m - 2) / 3 * (m - 3) / 4; }
-
-// smallest m in [lo, hi] with f(m) >= x  (f non-decreasing)
-template <typename F>
-__device__ __forceinline__ uint32_t lower_bound_fn(uint32_t lo, uint32_t hi, uint64_t x, F f)
-{
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (f(mid) >= x) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
-__global__ void __launch_bounds__(256) unrank_kernel(const int64_t *__restrict__ ranks, int64_t start, int64_t m,
-                                                     uint32_t n, uint4 *__restrict__ quartets)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    uint64_t r = (uint64_t)(ranks ? ranks[i] : start + i);
-    const uint64_t total = choose4(n);
-    // first id a: largest a with total - C(n-a,4) <= r  <=>  smallest m1 = n-a with C(m1,4) >= total - r ... (m1 maximal a)
-    const uint32_t m1 = lower_bound_fn(4u, n, total - r, [](uint32_t mm) { return choose4(mm); });
-    const uint32_t a = n - m1;
-    r -= total - choose4(m1);
-    const uint64_t x = choose3(m1 - 1) - r;                         // >= 1
-    const uint32_t m2 = lower_bound_fn(3u, m1 - 1, x, [](uint32_t mm) { return choose3(mm); });
-    const uint32_t b = n - m2;
-    r -= choose3(m1 - 1) - choose3(m2);
-    const uint64_t y = choose2(m2 - 1) - r;
-    const uint32_t m3 = lower_bound_fn(2u, m2 - 1, y, [](uint32_t mm) { return choose2(mm); });
-    const uint32_t c = n - m3;
-    r -= choose2(m2 - 1) - choose2(m3);
-    quartets[i] = make_uint4(a, b, c, c + 1 + (uint32_t)r);
-}
-
-cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint32_t ntips, uint32_t *d_quartets,
-                          cudaStream_t stream)
-{
-    if (m == 0) return cudaSuccess;
-    unrank_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(d_ranks, start, m, ntips,
-                                                                   reinterpret_cast<uint4 *>(d_quartets));
-    ++g_launches;
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
-// K2/K5: bootstrap replicate built on the device (reference resample_tmp_database +
-// jit_resample + jit_resolve_ambigs, run_inference.py:99-143, resample.py:20-64,
-// resolve_ambigs.py:12-36).  The host draws which locus fills instance i (the reference's
-// rng.choice); the device draws, from Philox4x32-10 streams keyed by the replicate's two seeds,
-//   * the random column order inside every locus instance (boot_columns_kernel), and
-//   * the coin that resolves every IUPAC two-base ambiguity cell (pack_gather_kernel),
-// and packs the replicate's bit-planes straight from the resident ASCII `seqarr`: the resampled
-// u8 matrix is never materialised.  oracle/boot_oracle.py restates the same streams in numpy.
-// ------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                           uint32_t k0, uint32_t k1)
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return c0;
-}
-
-// srccol[(tile_off[tile] + k*32) * 32 + locus_in_tile] = source column of rank k of that instance
-__global__ void __launch_bounds__(256) boot_columns_kernel(PlanDev plan, const uint32_t *__restrict__ src_start,
-                                                           uint32_t seed_shuffle, uint32_t *__restrict__ srccol)
-{
-    const uint32_t sl = blockIdx.x * blockDim.x + threadIdx.x;       // sorted locus index
-    if (sl >= (uint32_t)plan.ntiles * kTileLoci) return;
-    const uint32_t n = plan.loc_len[sl];
-    if (n == 0) return;
-    const uint32_t inst = plan.loc_run[sl];                            // instance index before the length sort
-    const uint32_t s0 = src_start[inst];
-    const uint32_t tile = sl / kTileLoci, within = sl % kTileLoci;
-    uint32_t *out = srccol + (size_t)plan.tile_off[tile] * kTileWords + within;
-    for (uint32_t j = 0; j < n; ++j) {
-        // rank of column j under the order (key, j): number of columns that sort before it
-        const uint32_t kj = philox4x32_10(inst, j, 0u, 0u, seed_shuffle, 0x5EEDu);
-        uint32_t rank = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            const uint32_t ki = philox4x32_10(inst, i, 0u, 0u, seed_shuffle, 0x5EEDu);
-            rank += (ki < kj || (ki == kj && i < j)) ? 1u : 0u;
-        }
-        out[(size_t)rank * kTileLoci] = s0 + j;
-    }
-}
-
-// ASCII cell -> code 0..3, or 4 = missing.  IUPAC two-base codes take one of their bases by coin
-// (tetrad/src/utils.py:14-21: R=G|A K=G|T S=G|C Y=T|C W=T|A M=C|A; coin set -> first base).
-__device__ __forceinline__ uint32_t decode_cell(uint32_t ch, uint32_t inst, uint32_t k, uint32_t tip, uint32_t seed_ambig)
-{
-    switch (ch) {
-    case 65u: return 0u; case 67u: return 1u; case 71u: return 2u; case 84u: return 3u;
-    case 0u: case 1u: case 2u: case 3u: return ch;                     // already recoded
-    case 82u: case 75u: case 83u: case 89u: case 87u: case 77u: {
-        const uint32_t coin = philox4x32_10(inst, k, tip, 1u, seed_ambig, 0xA3B1u) & 1u;
-        switch (ch) {
-        case 82u: return coin ? 2u : 0u;  case 75u: return coin ? 2u : 3u;  case 83u: return coin ? 2u : 1u;
-        case 89u: return coin ? 3u : 1u;  case 87u: return coin ? 3u : 0u;  default:  return coin ? 1u : 0u;
-        }
-    }
-    default: return 4u;
-    }
-}
-
-__global__ void __launch_bounds__(128) pack_gather_kernel(PlanDev plan, const uint8_t *__restrict__ seqarr,
-                                                          int64_t row_stride, const uint32_t *__restrict__ srccol,
-                                                          uint32_t seed_ambig, uint4 *__restrict__ planes)
-{
-    const int tile = blockIdx.x, tip = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t K = plan.tile_k[tile];
-    const uint32_t off = plan.tile_off[tile];
-    const uint8_t *row = seqarr + (int64_t)tip * row_stride;
-    uint4 *out = planes + (size_t)tip * plan.row_u4 + off;
-    const uint32_t l0 = (uint32_t)tile * kTileLoci + lane * 32;
-    for (uint32_t k = warp; k < K; k += 4) {
-        const uint32_t *cols = srccol + ((size_t)off + k * kTileWords) * kTileWords + lane * 32;
-        uint4 w = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 4
-        for (int b = 0; b < 32; ++b) {
-            if (k < __ldg(plan.loc_len + l0 + b)) {
-                const uint32_t code = decode_cell(row[__ldg(cols + b)], __ldg(plan.loc_run + l0 + b), k, (uint32_t)tip, seed_ambig);
-                const uint32_t bit = 1u << b;
-                w.x |= (code == 0u) ? bit : 0u;
-                w.y |= (code == 1u) ? bit : 0u;
-                w.z |= (code == 2u) ? bit : 0u;
-                w.w |= (code == 3u) ? bit : 0u;
-            }
-        }
-        out[k * kTileWords + lane] = w;
-    }
-}
-
-cudaError_t launch_boot_pack(const PlanDev &plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
-                             const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
-                             uint32_t *d_srccol, uint32_t *d_planes, cudaStream_t stream)
-{
-    if (plan.ntiles == 0 || ntips == 0) return cudaSuccess;
-    const unsigned nl = (unsigned)plan.ntiles * kTileLoci;
-    boot_columns_kernel<<<(nl + 255) / 256, 256, 0, stream>>>(plan, d_src_start, seed_shuffle, d_srccol);
-    ++g_launches;
-    dim3 grid((unsigned)plan.ntiles, (unsigned)ntips);
-    pack_gather_kernel<<<grid, 128, 0, stream>>>(plan, d_seqarr, row_stride, d_srccol, seed_ambig,
-                                                 reinterpret_cast<uint4 *>(d_planes));
-    ++g_launches;
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
 // K3: counts
 // ------------------------------------------------------------------------------------------
 // One warp resolves one quartet.  Lane l owns locus word l of every tile (32 loci).

@@ -17,14 +17,18 @@ struct PlanDev {
     const uint32_t *loc_start;  // [ntiles*1024] first column of sorted locus l (pad: 0)
     const uint32_t *loc_len;    // [ntiles*1024] columns of sorted locus l      (pad: 0)
     const uint32_t *loc_run;    // [ntiles*1024] index of the locus run before the length sort
+    const uint32_t *loc_pos;    // [ntiles*1024+1] columns of the sorted loci before l (prefix sum of loc_len)
     int      ntiles;
     uint32_t row_u4;            // uint4 per tip row
+    uint32_t ncols;             // columns of the replicate (sum of loc_len)
+    uint32_t nloci;             // locus runs (the tables are padded to ntiles*1024)
 };
 
-cudaError_t launch_pack(const PlanDev &plan, const uint8_t *d_tmparr, int64_t ntips,
+// tip rows [tip_lo, tip_hi) of the matrix at d_tmparr / d_seqarr -> the same rows of d_planes (both full-matrix bases)
+cudaError_t launch_pack(const PlanDev &plan, const uint8_t *d_tmparr, int64_t tip_lo, int64_t tip_hi,
                         int64_t row_stride, uint32_t *d_planes, cudaStream_t stream);
 
-cudaError_t launch_boot_pack(const PlanDev &plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
+cudaError_t launch_boot_pack(const PlanDev &plan, const uint8_t *d_seqarr, int64_t tip_lo, int64_t tip_hi, int64_t row_stride,
                              const uint32_t *d_src_start, uint32_t seed_shuffle, uint32_t seed_ambig,
                              uint32_t *d_srccol, uint32_t *d_planes, cudaStream_t stream);
 

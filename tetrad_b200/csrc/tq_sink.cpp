@@ -5,6 +5,7 @@
 //                    its wQMC weights from the parsed TSV, run_inference.py:262-297)
 //   tq_format_qmc    lines "a,b|c,d:weight" of the wQMC input (run_inference.py:305)
 #include "../../include/tetrad_b200.h"
+#include "tq_error.h"
 
 #include <cmath>
 #include <cstdio>
@@ -70,6 +71,21 @@ inline char *put_fixed(char *p, unsigned long long scaled, int digits)
 
 bool printable(double x) { return x >= 0.0 && x < 4.0e9; }   // NaN / inf / negative: not a score
 
+// A value the fast path does not take (NaN, inf, negative, >= 4e9) is written the way the reference's own formatting
+// would write it: printf's full decimal expansion, up to 316 characters for a finite double.  It goes through a
+// bounded temporary and is copied only if the caller's buffer still has room for it AND the rest of the row
+// (`tail` bytes); returns nullptr otherwise.
+char *put_odd(char *p, const char *end, double x, int digits, int tail)
+{
+    char tmp[400];
+    int n = snprintf(tmp, sizeof(tmp), "%.*f", digits, x);
+    if (n < 0) n = 0;
+    if (n > (int)sizeof(tmp) - 1) n = (int)sizeof(tmp) - 1;
+    if (end - p < n + tail) return nullptr;
+    memcpy(p, tmp, (size_t)n);
+    return p + n;
+}
+
 }  // namespace
 
 extern "C" {
@@ -77,15 +93,18 @@ extern "C" {
 int64_t tq_format_tsv(const uint32_t *quartets, const uint32_t *rstat, const double *rscor, int64_t m,
                       char *out, int64_t cap)
 {
-    if (m < 0 || (m > 0 && (!quartets || !rstat || !rscor || !out))) return TQ_EINVAL;
+    if (m < 0 || (m > 0 && (!quartets || !rstat || !rscor || !out))) return tq::set_error(TQ_EINVAL, "tq_format_tsv: bad arguments");
     char *p = out;
+    const char *end = out + cap;
     for (int64_t i = 0; i < m; ++i) {
-        if (cap - (p - out) < 160) return TQ_ENOMEM;      // longest possible row is < 160 bytes
+        // longest row of printable scores is < 160 bytes (4 x 10 + 3 x 17 + 2 x 10 digits, 9 separators)
+        if (end - p < 160) return tq::set_error(TQ_ENOMEM, "tq_format_tsv: output buffer too small at row %lld", (long long)i);
         for (int k = 0; k < 4; ++k) { p = put_uint(p, quartets[4 * i + k]); *p++ = '\t'; }
         for (int k = 0; k < 3; ++k) {
             const double x = rscor[3 * i + k];
             if (printable(x)) p = put_fixed(p, exact_round(x, 6), 6);
-            else p += snprintf(p, 64, "%.6f", x);
+            else if (!(p = put_odd(p, end, x, 6, 64)))      // 64: the rest of the row if every later score is printable
+                return tq::set_error(TQ_ENOMEM, "tq_format_tsv: row %lld holds a score of more than 17 characters (%g); buffer too small", (long long)i, x);
             *p++ = '\t';
         }
         p = put_uint(p, rstat[2 * i]); *p++ = '\t';
@@ -96,7 +115,7 @@ int64_t tq_format_tsv(const uint32_t *quartets, const uint32_t *rstat, const dou
 
 int tq_round_scores(const double *rscor, int64_t n, double *out)
 {
-    if (n < 0 || (n > 0 && (!rscor || !out))) return TQ_EINVAL;
+    if (n < 0 || (n > 0 && (!rscor || !out))) return tq::set_error(TQ_EINVAL, "tq_round_scores: bad arguments");
     for (int64_t i = 0; i < n; ++i) {
         const double x = rscor[i];
         // N / 10^6 with N < 2^53 is the correctly rounded value of the decimal text, i.e. what strtod returns
@@ -109,7 +128,7 @@ int64_t tq_qmc_weights(const uint32_t *quartets, const uint32_t *rstat, const do
                        int64_t min_snps, double min_ratio, uint32_t *tips_out, double *weight_out)
 {
     if (m < 0 || weights < 0 || weights > 3 || (m > 0 && (!quartets || !rstat || !rscor || !tips_out || !weight_out)))
-        return TQ_EINVAL;
+        return tq::set_error(TQ_EINVAL, "tq_qmc_weights: bad arguments");
     static const int order[3][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};   // split -> a,b|c,d (run_inference.py:41-45)
     if (min_snps < 1) min_snps = 1;
     int64_t n = 0;
@@ -143,10 +162,11 @@ int64_t tq_qmc_weights(const uint32_t *quartets, const uint32_t *rstat, const do
 
 static int64_t format_qmc_rows(const uint32_t *tips, const double *weight, const int64_t *rows, int64_t n, char *out, int64_t cap)
 {
-    if (n < 0 || (n > 0 && (!tips || !weight || !out))) return TQ_EINVAL;
+    if (n < 0 || (n > 0 && (!tips || !weight || !out))) return tq::set_error(TQ_EINVAL, "tq_format_qmc: bad arguments");
     char *p = out;
+    const char *end = out + cap;
     for (int64_t k = 0; k < n; ++k) {
-        if (cap - (p - out) < 128) return TQ_ENOMEM;
+        if (end - p < 128) return tq::set_error(TQ_ENOMEM, "tq_format_qmc: output buffer too small at line %lld", (long long)k);
         const int64_t i = rows ? rows[k] : k;
         p = put_uint(p, tips[4 * i]); *p++ = ',';
         p = put_uint(p, tips[4 * i + 1]); *p++ = '|';
@@ -154,7 +174,8 @@ static int64_t format_qmc_rows(const uint32_t *tips, const double *weight, const
         p = put_uint(p, tips[4 * i + 3]); *p++ = ':';
         const double w = weight[i];
         if (printable(w)) p = put_fixed(p, exact_round(w, 5), 5);
-        else p += snprintf(p, 64, "%.5f", w);
+        else if (!(p = put_odd(p, end, w, 5, 1)))
+            return tq::set_error(TQ_ENOMEM, "tq_format_qmc: line %lld holds a weight of more than 16 characters (%g); buffer too small", (long long)k, w);
         *p++ = '\n';
     }
     return (int64_t)(p - out);
@@ -167,7 +188,7 @@ int64_t tq_format_qmc(const uint32_t *tips, const double *weight, int64_t n, cha
 
 int64_t tq_format_qmc_rows(const uint32_t *tips, const double *weight, const int64_t *rows, int64_t n, char *out, int64_t cap)
 {
-    if (n > 0 && !rows) return TQ_EINVAL;
+    if (n > 0 && !rows) return tq::set_error(TQ_EINVAL, "tq_format_qmc_rows: rows is NULL");
     return format_qmc_rows(tips, weight, rows, n, out, cap);
 }
 

@@ -39,6 +39,29 @@ def _ctx(device: int) -> int:
     return _CTX[device]
 
 
+_UPLOAD_STREAMS: dict = {}
+
+
+def upload(array: np.ndarray, device):
+    """Host array -> device tensor without tying the host to the compute stream.  The copy runs on a side stream that
+    is otherwise idle (so a copy from pageable memory blocks the host only for its own duration, not until a 40 ms
+    resolve kernel ahead of it on the compute stream has finished) and the current stream waits for its event.  This
+    is what lets the replicate loop prepare replicate r + 1 while replicate r resolves."""
+    import torch
+    device = torch.device(device)
+    side = _UPLOAD_STREAMS.get(device)
+    if side is None:
+        side = _UPLOAD_STREAMS[device] = torch.cuda.Stream(device)
+    cur = torch.cuda.current_stream(device)
+    with torch.cuda.stream(side):
+        t = torch.from_numpy(array).to(device)
+        done = torch.cuda.Event()
+        done.record(side)
+    cur.wait_event(done)
+    t.record_stream(cur)
+    return t
+
+
 def _as_locus(tmpmap: np.ndarray):
     """(array kept alive, pointer, element stride) of the locus-id column tmpmap[:, 0]."""
     tmpmap = np.asarray(tmpmap)
@@ -142,69 +165,88 @@ class QuartetResolver:
         self.ntips = 0
         self.tmparr_dev = None
         self.seqarr_dev = None
+        self._plan_stream = None             # torch stream the plan's tables belong to
+        self._last_use = None                # event after the last resolve issued under another stream
+        self._plane_store = None
+        self._srccol = None
 
     # -- replicate state -----------------------------------------------------------------
     def _stream(self) -> int:
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def close(self):
+        """Destroy the plan.  Its device tables are stream-ordered memory of the stream the plan was created on
+        (``tq_plan_destroy`` frees them in that stream's order): a ``resolve`` issued under another torch stream is
+        ordered before the free through the event it left behind."""
         if self.plan is not None:
+            if self._last_use is not None and self._plan_stream is not None:
+                self._plan_stream.wait_event(self._last_use)
             self.lib.tq_plan_destroy(self.plan)
             self.plan = None
+            self._last_use = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
-    def load(self, tmparr, tmpmap) -> "QuartetResolver":
-        """Upload ``tmparr`` (numpy u8[n,S] or a CUDA uint8 tensor) and pack it."""
+    def _new_plan(self, create) -> None:
         torch = self.torch
-        locus_arr, locus_ptr, locus_stride = _as_locus(tmpmap)
         self.close()
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tq_plan_create(locus_ptr, locus_arr.shape[0], locus_stride,
-                                               self.device.index, self._stream(), ctypes.byref(h)))
+            self._plan_stream = torch.cuda.current_stream(self.device)
+            _lib.check(create(self._plan_stream.cuda_stream, ctypes.byref(h)))
         self.plan = h.value
         info = (ctypes.c_int64 * 8)()
         _lib.check(self.lib.tq_plan_info(self.plan, info))
         self.info = dict(ncols=info[0], nloci=info[1], ntiles=info[2], row_words=info[3],
                          max_len=info[4], padded_cols=info[5])
+
+    def _planes_for(self, ntips: int):
+        """Plane buffer of the replicate; reused between replicates while it is large enough."""
+        torch = self.torch
+        words = max(4, self.info["row_words"])
+        need = ntips * words
+        if self._plane_store is None or self._plane_store.numel() < need:
+            self._plane_store = torch.empty(need + need // 16, dtype=torch.int32, device=self.device)
+        return self._plane_store[:need].view(ntips, words)
+
+    def load(self, tmparr, tmpmap, tip_range=None) -> "QuartetResolver":
+        """Upload ``tmparr`` (numpy u8[n,S] or a CUDA uint8 tensor) and pack it.  ``tip_range=(lo, hi)`` packs only
+        those tip rows (the caller all-gathers the planes: ``replicate.ReplicatePipeline``)."""
+        torch = self.torch
+        locus_arr, locus_ptr, locus_stride = _as_locus(tmpmap)
+        self._new_plan(lambda stream, out: self.lib.tq_plan_create(locus_ptr, locus_arr.shape[0], locus_stride,
+                                                                   self.device.index, stream, out))
         if isinstance(tmparr, torch.Tensor):
             dev = tmparr.to(self.device, dtype=torch.uint8).contiguous()
         else:
-            host = np.ascontiguousarray(tmparr, dtype=np.uint8)
-            dev = torch.from_numpy(host).to(self.device, non_blocking=False)
+            dev = upload(np.ascontiguousarray(tmparr, dtype=np.uint8), self.device)
         if dev.ndim != 2 or dev.shape[1] != self.info["ncols"]:
             raise ValueError("tmparr must be u8[ntips, ncols] with ncols == len(tmpmap)")
         self.tmparr_dev = dev
         self.ntips = int(dev.shape[0])
-        self.planes = torch.empty((self.ntips, max(4, self.info["row_words"])), dtype=torch.int32,
-                                  device=self.device)
-        self.pack()
+        self.planes = self._planes_for(self.ntips)
+        self.pack(tip_range)
         return self
 
-    def load_bootstrap(self, seqarr, spans, lidxs, seed_shuffle: int, seed_ambig: int) -> "QuartetResolver":
+    def load_bootstrap(self, seqarr, spans, lidxs, seed_shuffle: int, seed_ambig: int, tip_range=None) -> "QuartetResolver":
         """Build a bootstrap replicate on the device (``tq_plan_create_runs`` + ``tq_boot_pack``).
 
         ``seqarr`` (numpy u8[n,S0] or a CUDA uint8 tensor already resident from an earlier call):
         the database's ASCII matrix (``-`` already mapped to ``N``; ambiguity codes unresolved);
         ``spans`` i64[L,2]; ``lidxs``: the loci drawn with replacement for this replicate
         (``rng.choice(L, L)`` of the reference, run_inference.py:117); the two seeds are the two
-        31-bit integers the reference draws next (:120, :123)."""
+        31-bit integers the reference draws next (:120, :123).  ``tip_range`` as in ``load``."""
         torch = self.torch
         spans = np.asarray(spans, dtype=np.int64)
         lidxs = np.asarray(lidxs, dtype=np.int64)
         lens = np.ascontiguousarray(spans[lidxs, 1] - spans[lidxs, 0], dtype=np.uint32)
         starts = np.ascontiguousarray(spans[lidxs, 0], dtype=np.uint32)
-        self.close()
-        h = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.tq_plan_create_runs(lens.ctypes.data, len(lens), self.device.index,
-                                                    self._stream(), ctypes.byref(h)))
-        self.plan = h.value
-        info = (ctypes.c_int64 * 8)()
-        _lib.check(self.lib.tq_plan_info(self.plan, info))
-        self.info = dict(ncols=info[0], nloci=info[1], ntiles=info[2], row_words=info[3],
-                         max_len=info[4], padded_cols=info[5])
+        self._new_plan(lambda stream, out: self.lib.tq_plan_create_runs(lens.ctypes.data, len(lens), self.device.index,
+                                                                        stream, out))
         if isinstance(seqarr, torch.Tensor):
             dev = seqarr if seqarr.device == self.device and seqarr.dtype == torch.uint8 and seqarr.is_contiguous() \
                 else seqarr.to(self.device, dtype=torch.uint8).contiguous()
@@ -212,20 +254,24 @@ class QuartetResolver:
             dev = torch.from_numpy(np.ascontiguousarray(seqarr, dtype=np.uint8)).to(self.device)
         self.seqarr_dev = dev
         self.ntips = int(dev.shape[0])
-        src = torch.from_numpy(starts.view(np.int32)).to(self.device)
-        scratch = torch.empty(max(1, self.info["padded_cols"]), dtype=torch.int32, device=self.device)
-        self.planes = torch.empty((self.ntips, max(4, self.info["row_words"])), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.tq_boot_pack(self.plan, dev.data_ptr(), self.ntips, dev.stride(0), src.data_ptr(),
-                                         int(seed_shuffle) & 0xFFFFFFFF, int(seed_ambig) & 0xFFFFFFFF,
-                                         scratch.data_ptr(), self.planes.data_ptr(), self._stream()))
+        src = upload(starts.view(np.int32), self.device)
+        need = max(1, self.info["padded_cols"])
+        if self._srccol is None or self._srccol.numel() < need:
+            self._srccol = torch.empty(need + need // 16, dtype=torch.int32, device=self.device)
+        self.planes = self._planes_for(self.ntips)
+        lo, hi = tip_range if tip_range is not None else (0, self.ntips)
+        _lib.check(self.lib.tq_boot_pack_rows(self.plan, dev.data_ptr(), self.ntips, dev.stride(0), lo, hi, src.data_ptr(),
+                                              int(seed_shuffle) & 0xFFFFFFFF, int(seed_ambig) & 0xFFFFFFFF,
+                                              self._srccol.data_ptr(), self.planes.data_ptr(), self._stream()))
         self.tmparr_dev = None
-        self._keep = (src, scratch)          # alive until the kernels have run
+        self._keep = src                     # alive until the kernels have run
         return self
 
-    def pack(self):
+    def pack(self, tip_range=None):
         """(Re)run K1 on the resident ``tmparr`` (exposed so bench.py can time it)."""
-        _lib.check(self.lib.tq_pack(self.plan, self.tmparr_dev.data_ptr(), self.ntips,
-                                    self.tmparr_dev.stride(0), self.planes.data_ptr(), self._stream()))
+        lo, hi = tip_range if tip_range is not None else (0, self.ntips)
+        _lib.check(self.lib.tq_pack_rows(self.plan, self.tmparr_dev.data_ptr(), self.ntips,
+                                         self.tmparr_dev.stride(0), lo, hi, self.planes.data_ptr(), self._stream()))
 
     # -- resolve -------------------------------------------------------------------------
     def resolve(self, quartets, subsample_snps: bool = True, want_counts: bool = False):
@@ -254,6 +300,10 @@ class QuartetResolver:
             counts.data_ptr() if want_counts else None,
             minrank.data_ptr() if want_counts else None, status.data_ptr(), self._stream()))
         self._last_status = status
+        cur = torch.cuda.current_stream(self.device)
+        if self._plan_stream is not None and cur != self._plan_stream:
+            self._last_use = torch.cuda.Event()
+            self._last_use.record(cur)
         if want_counts:
             return rstat, rscor, counts, minrank
         return rstat, rscor

@@ -83,6 +83,9 @@ def _format_parallel(call, nrows: int, row_bytes: int):
         hi = min(nrows, lo + _SINK_CHUNK)
         buf = ctypes.create_string_buffer(row_bytes * (hi - lo))
         n = call(lo, hi, buf)
+        if n == -4:                                        # TQ_ENOMEM: a row holds a non-score (inf, 1e300, ...) whose
+            buf = ctypes.create_string_buffer(1200 * (hi - lo))   # full decimal text is longer than the row budget
+            n = call(lo, hi, buf)
         if n < 0:
             from . import _lib
             _lib.check(int(n))
@@ -299,9 +302,22 @@ def infer_supertree(proj: Project, idx: int, weights: int, min_snps: int = 0, mi
 def draw_bootstrap(spans: np.ndarray, rng: np.random.Generator):
     """The three draws ``resample_tmp_database`` takes from the project's generator
     (run_inference.py:117, :120, :123): (lidxs, seed_shuffle, seed_ambig)."""
-    nloci = spans.shape[0]
-    lidxs = rng.choice(nloci, nloci, replace=True)
-    return lidxs, int(rng.integers(2**31)), int(rng.integers(2**31))
+    from .replicate import draw_bootstrap as _draw
+    return _draw(spans, rng)
+
+
+def agreed_seed(seed):
+    """The seed every rank builds the project's generator from.  A seeded project: its seed.  An unseeded one (a JSON
+    written by the reference, or by an older ``init``): fresh OS entropy -- drawn on rank 0 and broadcast when a
+    process group is up, because every rank replays the same draws (loci, Philox seeds, quartet ranks) from its own
+    copy of the generator and rank 0 writes the gathered shards under ITS quartet list."""
+    import torch.distributed as dist
+    if seed is not None:
+        return int(seed)
+    box = [int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0] >> np.uint64(1))]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast_object_list(box, src=0)
+    return box[0]
 
 
 def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int = 0, resolver=None,
@@ -315,25 +331,29 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
     the host builds ``tmparr``/``tmpmap`` (``resample_arrays``) and the engine packs them.
     ``save_invariants`` keeps every replicate's site-pattern count matrices, the deprecated API's option
     (deprecated/distributor.py:231-257 stores them as ``invariants/boot{k}`` u16[nquartets,16,16] in its HDF5):
-    here ``{name}.invariants_{rep}.npy``, u32[nquartets,16,16] (= ``mats[0]``; u32 because counts pass 65 535)."""
-    import torch
+    here ``{name}.invariants_{rep}.npy``, u32[nquartets,16,16] (= ``mats[0]``; u32 because counts pass 65 535).
+
+    The GPU side of a replicate is ``replicate.ReplicatePipeline`` (draw -> prepare -> resolve -> fetch, two engines
+    alternating): replicate r + 1 is drawn, planned and queued on the device while replicate r resolves, and the
+    sink of replicate r (TSV, wQMC input, wQMC, checkpoint) runs on worker threads beside both."""
+    import time
     import torch.distributed as dist
-    from . import sharding
+    from .replicate import ReplicatePipeline
     if save_invariants and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         raise NotImplementedError("save_invariants is a single-process option (1 KB per quartet is not gathered)")
 
     arrays = database.read_arrays(proj.database_file, ["seqarr", "spans", "tmparr", "tmpmap"])
-    if resolver is None:
-        from .resolve_quartets import QuartetResolver
-        resolver = QuartetResolver(device=device, seed=proj.random_seed or 0)
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
     if proj.bootstrap_rng is None:
         logger.info("starting quartet tree inference")
-        rng = np.random.default_rng(proj.random_seed)
+        rng = np.random.default_rng(agreed_seed(proj.random_seed))
     else:
         logger.info("continuing quartet tree inference")
         rng = proj.bootstrap_rng.to_rng()
+
+    pipe = ReplicatePipeline(arrays, proj.nsamples, proj.nqrts, proj.nqrts_total, proj.subsample_snps, device=device,
+                             seed=proj.random_seed or 0, resolver=resolver, device_bootstrap=device_bootstrap)
 
     from concurrent.futures import ThreadPoolExecutor
     # Two sink workers: the heavy part of a replicate's sink (TSV, wQMC input, wQMC itself) is independent of its
@@ -341,93 +361,49 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
     # (tree files and the checkpoint), so replicates still become durable in order (reference :396-407).
     pool = ThreadPoolExecutor(max_workers=2) if overlap_sink else None
     pending = []
-    exhaustive = proj.nqrts == proj.nqrts_total
-    gpu_index = getattr(getattr(resolver, "device", None), "index", None)      # None for CPU stand-ins (tests)
-    full = full_dev = None
-    if exhaustive and gpu_index is not None:
-        full_dev = combinations.device_quartets(proj.nsamples, gpu_index)       # unranked on the GPU, no upload
-        full = full_dev.cpu().numpy().view(np.uint32)
-    elif exhaustive:
-        full = combinations.all_quartets(proj.nsamples)
-    import time
-    on_device = device_bootstrap and hasattr(resolver, "load_bootstrap")
 
-    def draw_replicate(idx):
-        """Every draw replicate ``idx`` takes from the project's generator, in the reference's order (its quartet
-        generator is lazy: the quartet draw happens after the resampling draws), and the generator state after
-        them.  Host work only, so that it can run while the GPU resolves the previous replicate."""
-        boot = host_arrays = ranks = drawn = None
-        if idx and on_device:
-            boot = draw_bootstrap(arrays["spans"], rng)
-        elif idx:
-            host_arrays = resample_arrays(arrays["seqarr"], arrays["spans"], rng)
-        if full is None and gpu_index is not None:              # same draw as the reference, unranked on the GPU later
-            from math import comb
-            ranks = np.random.default_rng(rng).choice(comb(proj.nsamples, 4), size=proj.nqrts, replace=False)
-        elif full is None:
-            drawn = combinations.random_quartets(proj.nsamples, proj.nqrts, rng)
-        return dict(boot=boot, host_arrays=host_arrays, ranks=ranks, drawn=drawn, state=RNGStateModel.from_rng(rng))
-
-    draws = draw_replicate(proj.bootstrap_idx) if proj.bootstrap_idx <= nboots else None
+    draws = prep = None
+    if proj.bootstrap_idx <= nboots:
+        draws = pipe.draw(proj.bootstrap_idx, rng)
+        prep = pipe.prepare(draws)
     while proj.bootstrap_idx <= nboots:
         t_start = time.perf_counter()
-        if draws["boot"] is not None:
-            lidxs, seed_shuffle, seed_ambig = draws["boot"]
-            seq = getattr(resolver, "seqarr_dev", None)
-            resolver.load_bootstrap(seq if seq is not None else arrays["seqarr"], arrays["spans"], lidxs,
-                                    seed_shuffle, seed_ambig)
-        elif draws["host_arrays"] is not None:
-            resolver.load(*draws["host_arrays"])
-        else:
-            resolver.load(arrays["tmparr"], arrays["tmpmap"])
-        if full is not None:
-            quartets, q_dev = full, full_dev
-        elif draws["ranks"] is not None:
-            q_dev = combinations.device_quartets(proj.nsamples, gpu_index, ranks=draws["ranks"])
-            quartets = q_dev.cpu().numpy().view(np.uint32)
-        else:
-            quartets, q_dev = draws["drawn"], None
-        if q_dev is None:
-            q_dev = torch.from_numpy(quartets.view(np.int32))
-            if hasattr(resolver, "device"):
-                q_dev = q_dev.to(resolver.device)
-        t_prep = time.perf_counter()
-        invariants = None
-        if save_invariants:
-            rstat_d, rscor_d, counts_d, _ = resolver.resolve(q_dev, proj.subsample_snps, want_counts=True)
-            out, invariants = (rstat_d, rscor_d), counts_d
-        else:
-            out = sharding.resolve_sharded(q_dev, lambda q: resolver.resolve(q, proj.subsample_snps))
         idx = proj.bootstrap_idx
-        rng_state = draws["state"]                       # generator state after this replicate's draws
-        # the next replicate's host draws (rng.choice over the loci and over the quartet ranks) run while the GPU resolves
-        draws = draw_replicate(idx + 1) if idx + 1 <= nboots else None
-        if hasattr(resolver, "device"):
-            torch.cuda.synchronize(resolver.device)
+        out = pipe.resolve(prep, want_counts=save_invariants)          # asynchronous on the GPU
+        rng_state = draws["state"]                                     # generator state after this replicate's draws
+        # the next replicate: host draws and plan now, its device work queued behind this replicate's resolve
+        next_draws = next_prep = None
+        if idx + 1 <= nboots:
+            next_draws = pipe.draw(idx + 1, rng)
+            next_prep = pipe.prepare(next_draws)
+        t_next = time.perf_counter()
+        got = pipe.fetch(prep, out)                                    # rank 0: results on the host (synchronises)
         t_gpu = time.perf_counter()
         while len(pending) >= 2:
             pending.pop(0).result()                        # at most two replicates' sinks in flight
+        nq = 0
         if rank == 0:
-            rstat, rscor = out
-            # D2H here (the GPU is idle anyway until the next launch); formatting, wQMC and the
-            # checkpoint run on a worker thread while the next replicate is resolved (SURVEY H7)
-            if invariants is not None:
+            quartets, rstat, rscor = got
+            nq = len(quartets)
+            if save_invariants:
                 np.save(proj.workdir / f"{proj.name}.invariants_{idx}.npy",
-                        invariants.cpu().numpy().view(np.uint32).reshape(-1, 16, 16))
-            job = (idx, quartets, rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy(), rng_state)
+                        out[2].cpu().numpy().view(np.uint32).reshape(-1, 16, 16))
+            job = (idx, quartets, rstat, rscor, rng_state)
             if pool is not None:
                 pending.append(pool.submit(_sink_replicate, proj, *job, after=pending[-1] if pending else None))
             else:
                 _sink_replicate(proj, *job)
-        logger.info(f"finished rep {idx}: {len(quartets)} quartets, prepare {t_prep - t_start:.3f} s, resolve "
-                    f"{t_gpu - t_prep:.3f} s ({len(quartets) / max(t_gpu - t_prep, 1e-9):.3g} quartets/s), "
+        logger.info(f"finished rep {idx}: {nq} quartets, host part of the next replicate {t_next - t_start:.3f} s, "
+                    f"replicate wall {t_gpu - t_start:.3f} s ({nq / max(t_gpu - t_start, 1e-9):.3g} quartets/s), "
                     f"hand-off to sink {time.perf_counter() - t_gpu:.3f} s")
         proj.bootstrap_idx += 1
         proj.bootstrap_rng = rng_state
+        draws, prep = next_draws, next_prep
     for fut in pending:
         fut.result()
     if pool is not None:
         pool.shutdown()
+    pipe.close()
 
 
 def _sink_replicate(proj: Project, idx: int, quartets, rstat, rscor, rng_state, after=None) -> None:

@@ -47,7 +47,12 @@ def init_database(data: Path, out: Path, rng) -> dict:
 
 
 def write_database(project) -> None:
-    """Fill the project's derived fields and write its database (reference :179-195)."""
+    """Fill the project's derived fields and write its database (reference :179-195).  A project created without
+    ``-r`` gets a concrete seed drawn from the OS here and kept in its JSON: ``run`` then reproduces, and the ranks of
+    a multi-GPU run (one process each, every one drawing from its own copy of the project's generator) agree."""
+    if project.random_seed is None:
+        project.random_seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0] >> np.uint64(1))
+        logger.info(f"no random seed given: drew {project.random_seed} (recorded in the project file)")
     info = init_database(project.data, project.database_file, project.random_seed)
     nsamples = len(info["names"])
     nqrts, nqrts_total = get_nquartets(nsamples, project.nquartets)
