@@ -254,7 +254,7 @@ def ncu_record(config: str, subsample: bool):
     return json.loads(path.read_text()) if path.exists() else None
 
 
-def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local, subsample=True):
+def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local, subsample=True, kernel=None):
     peak_gbs, peak_src, pipes = measured_peaks(lib, local)
     kern_s = kern_ms * 1e-3
     alg = algorithmic_bytes_per_quartet(ncols, subsample)
@@ -265,7 +265,7 @@ def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local
     imma_per_quartet = 64.0 * products
     alu_per_quartet = 32.0 * (320.0 * products + (36.0 * chunks if subsample else 0.0))
     block = {
-        "bound": "hbm", "kernel": lib.tq_last_kernel().decode(), "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "bound": "hbm", "kernel": kernel or lib.tq_last_kernel().decode(), "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": rec.get("dram_bytes_per_launch") if rec else None, "peak_source": peak_src,
         "algorithmic_bytes_per_quartet": alg, "quartets_per_launch": quartets_per_launch, "kernel_ms": kern_ms,
         "note": "SURVEY 8(d) accounting: every quartet counts its four tip rows once; the rows come from L2 (and, past "
@@ -335,6 +335,7 @@ def bench_static(config, world, rank, local, dev, lib, steps, warmup, subsample=
     total_ms = max_over_ranks(sum(e[0].elapsed_time(e[2]) for e in events), world, dev)
     kern_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in events)
     res = dict(Q=Q, value=Q * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps, kern_ms=kern_ms,
+               kernel=lib.tq_last_kernel().decode(),
                quartets_per_launch=hi - lo, launches=int(launches), ncols=int(tmparr.shape[1]), info=dict(eng.info),
                tmparr=tmparr, tmpmap=tmpmap, quartets=quartets)
     if e2e:
@@ -360,7 +361,7 @@ def bench_static(config, world, rank, local, dev, lib, steps, warmup, subsample=
     return res
 
 
-def bench_replicates(config, world, rank, local, dev, lib, steps, warmup):
+def bench_replicates(config, world, rank, local, dev, lib, steps, warmup, sampler="device"):
     """Bootstrap replicates of `config` through ReplicatePipeline (strong scaling)."""
     import torch
     from tetrad_b200.replicate import ReplicatePipeline
@@ -368,25 +369,27 @@ def bench_replicates(config, world, rank, local, dev, lib, steps, warmup):
     db = synth.config_arrays(config, seed=1234)
     arrays = {k: db[k] for k in ("seqarr", "spans", "tmparr", "tmpmap")}
     n, Q = cfg["ntips"], cfg["nquartets"]
-    pipe = ReplicatePipeline(arrays, n, Q, comb(n, 4), True, device=local, seed=0, timing=True)
+    pipe = ReplicatePipeline(arrays, n, Q, comb(n, 4), True, device=local, seed=0, timing=True, sampler=sampler)
     stream = torch.cuda.current_stream(dev)
     rng = np.random.default_rng(42)                      # every rank replays the same generator
 
     def run(k, first_idx, fetch, draws_ready=None):
-        """k replicates, pipelined as run_inference does; returns the Prepared records (events inside)."""
+        """k replicates, pipelined as run_inference does (replicate r + 1 is prepared and launched before the results
+        of replicate r are read); returns the Prepared records (events inside) and the last fetched results."""
+        def get_draw(i):
+            return draws_ready[i] if draws_ready else pipe.draw(first_idx + i, rng)
         preps, got = [], None
-        draws = draws_ready[0] if draws_ready else pipe.draw(first_idx, rng)
-        prep = pipe.prepare(draws)
+        prep = pipe.prepare(get_draw(0))
+        out = pipe.resolve(prep)
         for i in range(k):
-            out = pipe.resolve(prep)
-            nxt = None
+            nprep = nout = None
             if i + 1 < k:
-                nd = draws_ready[i + 1] if draws_ready else pipe.draw(first_idx + i + 1, rng)
-                nxt = pipe.prepare(nd)
+                nprep = pipe.prepare(get_draw(i + 1))
+                nout = pipe.resolve(nprep)
             if fetch:
                 got = pipe.fetch(prep, out)
             preps.append(prep)
-            prep = nxt
+            prep, out = nprep, nout
         return preps, got
 
     run(max(3, warmup), 1, fetch=False)
@@ -421,11 +424,11 @@ def bench_replicates(config, world, rank, local, dev, lib, steps, warmup):
         quartets, rstat, rscor = got
         assert quartets.shape == (Q, 4) and rstat.shape == (Q, 2) and rscor.shape == (Q, 3) and np.isfinite(rscor).all()
     lpad = info["ntiles"] * 1024
-    h2d = (4 * lpad + 2 * info["ntiles"] + 2) * 4 + cfg["nloci"] * 4 + Q * 8       # plan tables, drawn loci, quartet ranks
+    h2d = (4 * lpad + 2 * info["ntiles"] + 2) * 4 + cfg["nloci"] * 4 + (Q * 8 if sampler == "numpy" else 0)   # plan tables, drawn loci (, quartet ranks)
     d2h = Q * 32 + Q * 16                                                          # results + quartet ids, rank 0
     res = dict(Q=Q, value=Q * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps, kern_ms=kern_ms,
                quartets_per_launch=-(-Q // world), launches=int(launches), ncols=int(info["ncols"]), info=info,
-               clocks=clocks, wall=wall,
+               clocks=clocks, wall=wall, kernel=lib.tq_last_kernel().decode(), sampler=sampler,
                replicate={"prepare_ms": prepare_ms, "resolve_ms": kern_ms, "gather_ms": gather_ms,
                           "note": "device time of one rank's share of a replicate (CUDA events, rank 0): bootstrap column "
                                   "orders + planes of this rank's tip rows + all-gather + unranking | resolve of Q/N "
@@ -447,7 +450,7 @@ def run_ours(args):
     replicate_mode = cfg["nboots"] > 0
     sampler = None
     if replicate_mode:
-        res = bench_replicates(args.config, world, rank, local, dev, lib, args.steps, args.warmup)
+        res = bench_replicates(args.config, world, rank, local, dev, lib, args.steps, args.warmup, sampler=args.sampler)
         clocks, wall = res["clocks"], res["wall"]
     else:
         sampler = ClockSampler(local)
@@ -459,14 +462,15 @@ def run_ours(args):
     extra = {}
     if world == 1 and args.config == DEFAULT_CONFIG and not args.quick:
         c2 = bench_static("C2", world, rank, local, dev, lib, 10, 3)
-        roof, bind = roofline_block("C2", c2["ncols"], c2["quartets_per_launch"], c2["kern_ms"], c2["info"], lib, local)
+        roof, bind = roofline_block("C2", c2["ncols"], c2["quartets_per_launch"], c2["kern_ms"], c2["info"], lib, local,
+                                    kernel=c2["kernel"])
         extra["c2"] = {"config": describe("C2"), "value": c2["value"], "ms_per_step": c2["ms_per_step"], "e2e": c2["e2e"],
                        "roofline": roof, "binding": bind,
                        "note": "BASELINE configs[1] (the 1-B200 shape): replicate 0 re-resolved against the resident matrix, "
                                "L2 flushed between steps"}
         fm = bench_static("C2", world, rank, local, dev, lib, 5, 3, subsample=False, e2e=False)
         roof, bind = roofline_block("C2", fm["ncols"], fm["quartets_per_launch"], fm["kern_ms"], fm["info"], lib, local,
-                                    subsample=False)
+                                    subsample=False, kernel=fm["kernel"])
         extra["full_mode"] = {"config": describe("C2", subsample=False), "value": fm["value"], "ms_per_step": fm["ms_per_step"],
                               "roofline": roof, "binding": bind,
                               "note": "subsample_snps=False (full_chunk_to_matrices, the CLI's default mode) at the C2 shape"}
@@ -476,7 +480,7 @@ def run_ours(args):
         return
 
     roofline, binding = roofline_block(args.config, res["ncols"], res["quartets_per_launch"], res["kern_ms"], res["info"],
-                                       lib, local)
+                                       lib, local, kernel=res["kernel"])
     cpu = None
     if world == 1 and not args.no_cpu:
         quartets = res.get("quartets")
@@ -493,6 +497,9 @@ def run_ours(args):
              "parallelism": f"quartet ranges x{world} (contiguous shard per rank), NCCL gather to rank 0" +
                             (", bootstrap planes packed by tip-row shares + NCCL all-gather" if replicate_mode and world > 1 else ""),
              "quartets_per_step": res["Q"]}
+    if replicate_mode:
+        setup["quartet_sampler"] = res["sampler"] + (" (keyed permutation on the device, one 63-bit draw per replicate)"
+                                                      if res["sampler"] == "device" else " (the reference's rng.choice on the host)")
     line = {
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
@@ -524,6 +531,8 @@ def main():
     ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(synth.CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sampler", default="device", choices=["device", "numpy"],
+                    help="random quartet samples of the replicate loop: device (default of the CLI) or the reference's host draw")
     ap.add_argument("--quick", action="store_true", help="skip the extra c2 / full_mode blocks of the default config")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -102,6 +102,16 @@ int tq_pack_rows(const tq_plan *plan, const uint8_t *d_tmparr, int64_t ntips, in
 int tq_unrank(int device, const int64_t *d_ranks, int64_t start, int64_t m, int64_t ntips,
               uint32_t *d_quartets, void *stream);
 
+/* Random quartet sample without a host draw (scales with the number of GPUs; the reference's host draw,
+ * rng.choice(C(n,4), Q, replace=False) at tetrad/src/combinations.py:109-114, is serial and costs 0.13 s per million
+ * quartets): quartet i of the sample is unrank(pi_key(i)) with pi_key a keyed pseudo-random permutation of
+ * [0, C(ntips,4)) (6-round Feistel network, cycle-walked).  Writes quartets start .. start + m - 1 of the sample to
+ * d_quartets u32[m][4]; distinct indices give distinct quartets.  Same distribution as the reference's draw, another
+ * stream (like the within-locus shuffles); tq_unrank with uploaded ranks reproduces the reference's. */
+int tq_sample_quartets(int device, int64_t start, int64_t m, int64_t ntips, uint64_t key, uint32_t *d_quartets, void *stream);
+/* the ranks pi_key(start .. start + m - 1) themselves, computed on the host (tests; no kernel) */
+int tq_sample_ranks_host(int64_t start, int64_t m, int64_t ntips, uint64_t key, int64_t *h_ranks);
+
 /* ------------------------------------------------------------------------------------------
  * K2/K5: bootstrap replicate packed on the device.  Replaces resample_tmp_database + jit_resample +
  * jit_resolve_ambigs (run_inference.py:99-143, tetrad/jit/resample.py:20-64,

@@ -127,6 +127,10 @@ def _declare(lib):
     lib.tq_qmc_weights.argtypes = [vp, vp, vp, i64, i32, i64, c.c_double, vp, vp]
     lib.tq_unrank.restype = i32
     lib.tq_unrank.argtypes = [i32, vp, i64, i64, i64, vp, vp]
+    lib.tq_sample_quartets.restype = i32
+    lib.tq_sample_quartets.argtypes = [i32, i64, i64, i64, u64, vp, vp]
+    lib.tq_sample_ranks_host.restype = i32
+    lib.tq_sample_ranks_host.argtypes = [i64, i64, i64, u64, vp]
     lib.tq_boot_pack.restype = i32
     lib.tq_boot_pack.argtypes = [vp, vp, i64, i64, vp, c.c_uint32, c.c_uint32, vp, vp, vp]
     lib.tq_pack.restype = i32
@@ -150,7 +154,7 @@ def _declare(lib):
 
 
 EXPORTS = [
-    "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_set_option", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank",
+    "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_set_option", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank", "tq_sample_quartets", "tq_sample_ranks_host",
     "tq_plan_destroy",
     "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_pack_rows", "tq_boot_pack_rows", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
     "tq_ctx_last_traffic", "tq_microbench", "tq_format_tsv", "tq_round_scores", "tq_format_qmc", "tq_format_qmc_rows", "tq_qmc_weights",

@@ -27,6 +27,9 @@ def _parser() -> ArgumentParser:
     init.add_argument("-r", "--random-seed", type=int)
     init.add_argument("-x", "--weights", type=int, default=1)
     init.add_argument("-s", "--subsample-snps", action="store_true")
+    init.add_argument("--quartet-sampler", choices=["device", "numpy"], default="device",
+                      help="random quartet samples: keyed permutation on the GPU (default; scales with the number of GPUs) "
+                           "or the reference's host draw rng.choice (same sample as the reference for the same seed)")
     run = sub.add_parser("run", help="run tree inference on a project")
     run.add_argument("json", type=Path)
     run.add_argument("-c", "--cores", type=int, default=0, help="ignored: work runs on the GPU(s)")
@@ -85,7 +88,7 @@ def main(argv=None) -> int:
         from .write_database import write_database
         proj = Project(version=__version__, data=args.data, name=args.name, workdir=args.workdir,
                        subsample_snps=args.subsample_snps, weights=args.weights, nquartets=int(args.nquartets),
-                       random_seed=args.random_seed)
+                       random_seed=args.random_seed, quartet_sampler=args.quartet_sampler)
         write_database(proj)
         proj.save_json()
         return 0

@@ -94,3 +94,17 @@ def device_quartets(nsamples: int, device: int = 0, ranks=None, start: int = 0, 
     out = torch.empty((m, 4), dtype=torch.int32, device=dev)
     _lib.check(lib.tq_unrank(device, None, start, m, nsamples, out.data_ptr(), stream))
     return out
+
+
+def device_sample(nsamples: int, key: int, count: int, device: int = 0, start: int = 0):
+    """``count`` quartets of the keyed random sample (``tq_sample_quartets``): quartet i = unrank(pi_key(i)), pi_key a
+    pseudo-random permutation of all C(n,4) ranks, so the quartets are distinct and any index range can be produced
+    on any GPU with no host draw and no upload.  int32 CUDA tensor [count, 4]."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", device)
+    out = torch.empty((count, 4), dtype=torch.int32, device=dev)
+    _lib.check(lib.tq_sample_quartets(device, start, count, nsamples, int(key) & (2**64 - 1), out.data_ptr(),
+                                      torch.cuda.current_stream(dev).cuda_stream))
+    return out

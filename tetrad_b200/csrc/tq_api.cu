@@ -382,6 +382,31 @@ int tq_unrank(int device, const int64_t *d_ranks, int64_t start, int64_t m, int6
     return TQ_OK;
 }
 
+int tq_sample_quartets(int device, int64_t start, int64_t m, int64_t ntips, uint64_t key, uint32_t *d_quartets, void *stream)
+{
+    if (m < 0 || start < 0 || ntips < 4 || ntips > 65535)
+        return fail(TQ_EINVAL, "tq_sample_quartets: bad sizes (start=%lld m=%lld ntips=%lld)", (long long)start, (long long)m, (long long)ntips);
+    if (m == 0) return TQ_OK;
+    if (!d_quartets || ((uintptr_t)d_quartets & 15u)) return fail(TQ_EINVAL, "tq_sample_quartets: d_quartets must be a 16-byte aligned device pointer");
+    const uint64_t n = (uint64_t)ntips, total = n * (n - 1) / 2 * (n - 2) / 3 * (n - 3) / 4;
+    if (total >= ((uint64_t)1 << 32)) return fail(TQ_EINVAL, "tq_sample_quartets: C(%lld,4) >= 2^32 (the reference asserts the same)", (long long)ntips);
+    if ((uint64_t)start + (uint64_t)m > total)
+        return fail(TQ_EINVAL, "tq_sample_quartets: sample indices [%lld, %lld) exceed C(%lld,4)", (long long)start, (long long)(start + m), (long long)ntips);
+    DeviceGuard guard(device);
+    TQ_CUDA(tq::launch_sample_unrank(start, m, (uint32_t)ntips, key, d_quartets, (cudaStream_t)stream));
+    return TQ_OK;
+}
+
+int tq_sample_ranks_host(int64_t start, int64_t m, int64_t ntips, uint64_t key, int64_t *h_ranks)
+{
+    if (m < 0 || start < 0 || ntips < 4 || ntips > 65535 || (m > 0 && !h_ranks)) return fail(TQ_EINVAL, "tq_sample_ranks_host: bad arguments");
+    const uint64_t n = (uint64_t)ntips, total = n * (n - 1) / 2 * (n - 2) / 3 * (n - 3) / 4;
+    if (total >= ((uint64_t)1 << 32) || (uint64_t)start + (uint64_t)m > total)
+        return fail(TQ_EINVAL, "tq_sample_ranks_host: sample indices [%lld, %lld) exceed C(%lld,4)", (long long)start, (long long)(start + m), (long long)ntips);
+    tq::sample_ranks_host(start, m, (uint32_t)ntips, key, h_ranks);
+    return TQ_OK;
+}
+
 int tq_boot_pack_rows(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntips, int64_t row_stride,
                       int64_t tip_lo, int64_t tip_hi, const uint32_t *d_src_start, uint32_t seed_shuffle,
                       uint32_t seed_ambig, uint32_t *d_srccol, uint32_t *d_planes, void *stream)

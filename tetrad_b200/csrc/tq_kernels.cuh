@@ -41,6 +41,11 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
 cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint32_t ntips, uint32_t *d_quartets,
                           cudaStream_t stream);
 
+cudaError_t launch_sample_unrank(int64_t start, int64_t m, uint32_t ntips, uint64_t key, uint32_t *d_quartets,
+                                 cudaStream_t stream);
+
+void sample_ranks_host(int64_t start, int64_t m, uint32_t ntips, uint64_t key, int64_t *out);
+
 cudaError_t run_microbench(int kind, double *result);
 
 extern std::atomic<int64_t> g_launches;      // kernels launched by this library since load

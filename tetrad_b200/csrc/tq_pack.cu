@@ -264,6 +264,86 @@ __global__ void __launch_bounds__(256) unrank_kernel(const int64_t *__restrict__
     quartets[i] = make_uint4(a, b, c, c + 1 + (uint32_t)r);
 }
 
+// ------------------------------------------------------------------------------------------
+// Random quartet sample without a host draw.  The reference draws rng.choice(C(n,4), Q, replace=False) on the host
+// (tetrad/src/combinations.py:109-114) -- 0.13 s per million quartets of 64.7 M, serial, which is what an 8-GPU
+// replicate loop would wait for.  Here quartet i of a replicate's sample is unrank(pi_key(i)), pi_key a keyed
+// pseudo-random PERMUTATION of [0, C(n,4)): a 6-round Feistel network on ceil(log2 C(n,4)) (rounded up to even) bits,
+// cycle-walked into the range.  Distinct i give distinct quartets by construction, the first Q images of a random
+// permutation are a uniform random Q-subset in random order, any rank computes any index range on its own, and nothing
+// is uploaded.  oracle/sample_oracle.py restates pi in numpy (bit-exact test + uniformity test).
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+__host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t x, uint64_t total, uint32_t half, uint32_t k0, uint32_t k1)
+{
+    const uint32_t mask = (uint32_t)((1ull << half) - 1ull);
+    do {
+        uint32_t L = (uint32_t)(x >> half), R = (uint32_t)x & mask;
+#pragma unroll
+        for (uint32_t r = 0; r < 6; ++r) {
+            const uint32_t f = fmix32(fmix32(R ^ k0 ^ (r * 0x9E3779B9u)) + k1) & mask;
+            const uint32_t nr = L ^ f;
+            L = R; R = nr;
+        }
+        x = ((uint64_t)L << half) | R;
+    } while (x >= total);
+    return x;
+}
+
+__device__ __forceinline__ uint4 unrank_quartet(uint64_t r, uint32_t n)
+{
+    const uint64_t total = choose4(n);
+    const uint32_t m1 = lower_bound_fn(4u, n, total - r, [](uint32_t mm) { return choose4(mm); });
+    const uint32_t a = n - m1;
+    r -= total - choose4(m1);
+    const uint64_t x = choose3(m1 - 1) - r;
+    const uint32_t m2 = lower_bound_fn(3u, m1 - 1, x, [](uint32_t mm) { return choose3(mm); });
+    const uint32_t b = n - m2;
+    r -= choose3(m1 - 1) - choose3(m2);
+    const uint64_t y = choose2(m2 - 1) - r;
+    const uint32_t m3 = lower_bound_fn(2u, m2 - 1, y, [](uint32_t mm) { return choose2(mm); });
+    const uint32_t c = n - m3;
+    r -= choose2(m2 - 1) - choose2(m3);
+    return make_uint4(a, b, c, c + 1 + (uint32_t)r);
+}
+
+__global__ void __launch_bounds__(256) sample_unrank_kernel(int64_t start, int64_t m, uint32_t n, uint32_t half, uint32_t k0,
+                                                            uint32_t k1, uint4 *__restrict__ quartets)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    quartets[i] = unrank_quartet(feistel_permute((uint64_t)(start + i), choose4(n), half, k0, k1), n);
+}
+
+// host twin of the permutation (CPU tests of the sampler; no kernel)
+void sample_ranks_host(int64_t start, int64_t m, uint32_t ntips, uint64_t key, int64_t *out)
+{
+    const uint64_t n = ntips, total = n * (n - 1) / 2 * (n - 2) / 3 * (n - 3) / 4;
+    uint32_t bits = 2;
+    while ((1ull << bits) < total) ++bits;
+    bits += bits & 1u;
+    for (int64_t i = 0; i < m; ++i)
+        out[i] = (int64_t)feistel_permute((uint64_t)(start + i), total, bits / 2, (uint32_t)key, (uint32_t)(key >> 32));
+}
+
+cudaError_t launch_sample_unrank(int64_t start, int64_t m, uint32_t ntips, uint64_t key, uint32_t *d_quartets, cudaStream_t stream)
+{
+    if (m == 0) return cudaSuccess;
+    const uint64_t n = ntips, total = n * (n - 1) / 2 * (n - 2) / 3 * (n - 3) / 4;
+    uint32_t bits = 2;
+    while ((1ull << bits) < total) ++bits;
+    bits += bits & 1u;
+    sample_unrank_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(start, m, ntips, bits / 2, (uint32_t)key, (uint32_t)(key >> 32),
+                                                                          reinterpret_cast<uint4 *>(d_quartets));
+    ++g_launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint32_t ntips, uint32_t *d_quartets,
                           cudaStream_t stream)
 {

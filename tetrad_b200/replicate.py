@@ -11,11 +11,19 @@ ipyparallel engines that each re-read the database (:184-251), collect.  Here on
              the per-replicate prepare shrinks with the number of GPUs like the resolve does;
 ``resolve``  this rank's contiguous quartet range (``sharding.shard_range``) + one gather of the 32 B/quartet results
              to rank 0;
-``fetch``    rank 0 only: results (and the quartet ids the sink prints) to the host.
+``fetch``    rank 0 only: results (and the quartet ids the sink prints) to the host -- copied on a side stream
+             behind the replicate's own completion event, so the next replicate's kernels are not waited for.
 
-Two engines alternate, so ``prepare(r + 1)`` is issued while ``resolve(r)`` is still running: the host part of the
-next replicate (draws, plan) overlaps the kernel, and the device goes from one replicate's resolve straight into the
-next one's pack without waiting for the host.  ``run_inference`` and ``bench.py`` both drive this class.
+Two engines alternate, so ``prepare(r + 1)`` and ``resolve(r + 1)`` are issued while replicate r is still running: the
+host part of the next replicate (draws, plan) overlaps the kernel, and the device goes from one replicate's resolve
+straight into the next one's pack and resolve without waiting for the host.  ``run_inference`` and ``bench.py`` both
+drive this class.
+
+Random quartet samples (``nquartets < C(n,4)``): ``sampler="device"`` (default) takes ONE 63-bit key per replicate from
+the project's generator and lets the device produce the sample (``tq_sample_quartets``: a keyed permutation of all
+ranks, nothing drawn or uploaded per quartet); ``sampler="numpy"`` takes the reference's own draw,
+``rng.choice(C(n,4), Q, replace=False)`` (tetrad/src/combinations.py:109-114) -- the same sample as the reference for
+the same seed, but 0.13 s of serial host time per million quartets, which an 8-GPU loop would spend waiting.
 """
 from __future__ import annotations
 
@@ -45,13 +53,16 @@ class Prepared:
     quartets: np.ndarray = None     # host u32 [Q, 4] (exhaustive list, CPU stand-ins, or filled by fetch)
     q_host_pinned: object = None    # pinned staging + event of the async D2H copy of q_dev (rank 0)
     q_event: object = None
+    done: object = None             # event after this replicate's resolve + gather on the compute stream
+    fetched: object = None          # event after the D2H copies of its results on the copy stream (rank 0)
+    host: dict = field(default_factory=dict)
     events: dict = field(default_factory=dict)
 
 
 class ReplicatePipeline:
     def __init__(self, arrays: dict, nsamples: int, nqrts: int, nqrts_total: int, subsample_snps: bool,
                  device: int = 0, seed: int = 0, resolver=None, device_bootstrap: bool = True,
-                 shard_pack: bool = True, timing: bool = False):
+                 shard_pack: bool = True, timing: bool = False, sampler: str = "device"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -59,6 +70,9 @@ class ReplicatePipeline:
         self.nsamples, self.nqrts, self.subsample = int(nsamples), int(nqrts), bool(subsample_snps)
         self.exhaustive = int(nqrts) == int(nqrts_total)
         self.timing = timing
+        if sampler not in ("device", "numpy"):
+            raise ValueError(f"no quartet sampler {sampler!r}")
+        self.sampler = sampler
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         if resolver is None:
@@ -80,23 +94,25 @@ class ReplicatePipeline:
             self.full_dev = torch.from_numpy(self.full.view(np.int32))
         self.copy_stream = torch.cuda.Stream(self.device) if self.gpu_index is not None else None
         self._seq_dev = None
-        self._pinned_q = {}                 # engine slot -> pinned staging of the quartet ids (rank 0)
+        self._pinned = {}                   # (what, engine slot) -> pinned staging buffers of rank 0's D2H copies
 
     # -- host draws ----------------------------------------------------------------------
     def draw(self, idx: int, rng: np.random.Generator) -> dict:
         """Every draw replicate ``idx`` takes from the project's generator, in the reference's order (its quartet
         generator is lazy: the quartet draw happens after the resampling draws), and the generator state after them."""
         from .run_inference import resample_arrays
-        boot = host_arrays = ranks = drawn = None
+        boot = host_arrays = ranks = drawn = key = None
         if idx and self.on_device:
             boot = draw_bootstrap(self.arrays["spans"], rng)
         elif idx:
             host_arrays = resample_arrays(self.arrays["seqarr"], self.arrays["spans"], rng)
-        if self.full is None and self.gpu_index is not None:    # same draw as the reference, unranked on the GPU later
+        if self.full is None and self.gpu_index is not None and self.sampler == "device":
+            key = int(rng.integers(2**63))                      # one draw; the device derives the sample from it
+        elif self.full is None and self.gpu_index is not None:  # same draw as the reference, unranked on the GPU later
             ranks = np.random.default_rng(rng).choice(comb(self.nsamples, 4), size=self.nqrts, replace=False)
         elif self.full is None:
             drawn = combinations.random_quartets(self.nsamples, self.nqrts, rng)
-        return dict(idx=idx, boot=boot, host_arrays=host_arrays, ranks=ranks, drawn=drawn,
+        return dict(idx=idx, boot=boot, host_arrays=host_arrays, ranks=ranks, drawn=drawn, key=key,
                     state=RNGStateModel.from_rng(rng))
 
     # -- device prepare ------------------------------------------------------------------
@@ -129,14 +145,18 @@ class ReplicatePipeline:
             self._allgather_planes(eng)
         if self.full is not None:
             prep.quartets, prep.q_dev = self.full, self.full_dev
-        elif draws["ranks"] is not None:
-            prep.q_dev = combinations.device_quartets(self.nsamples, self.gpu_index, ranks=draws["ranks"])
+        elif draws["ranks"] is not None or draws["key"] is not None:
+            if draws["key"] is not None:
+                prep.q_dev = combinations.device_sample(self.nsamples, draws["key"], self.nqrts, self.gpu_index)
+            else:
+                prep.q_dev = combinations.device_quartets(self.nsamples, self.gpu_index, ranks=draws["ranks"])
             if self.rank == 0:                  # the sink prints the tip ids: copy them back beside the resolve
                 done = self._event()
                 slot = idx % len(self.engines)
-                if slot not in self._pinned_q or self._pinned_q[slot].shape != prep.q_dev.shape:
-                    self._pinned_q[slot] = torch.empty(prep.q_dev.shape, dtype=torch.int32, pin_memory=True)
-                prep.q_host_pinned = self._pinned_q[slot]
+                key = ("q", slot)
+                if key not in self._pinned or self._pinned[key].shape != prep.q_dev.shape:
+                    self._pinned[key] = torch.empty(prep.q_dev.shape, dtype=torch.int32, pin_memory=True)
+                prep.q_host_pinned = self._pinned[key]
                 with torch.cuda.stream(self.copy_stream):
                     self.copy_stream.wait_event(done)
                     prep.q_host_pinned.copy_(prep.q_dev, non_blocking=True)
@@ -191,22 +211,55 @@ class ReplicatePipeline:
         if self.timing and self.gpu_index is not None:
             prep.events.setdefault("resolve_end", self._event())
             prep.events["gather_end"] = self._event()
+        if self.gpu_index is not None:
+            prep.done = self.torch.cuda.Event()
+            prep.done.record(self.torch.cuda.current_stream(self.device))
+            if out is not None and not want_counts:
+                self._start_fetch(prep, out)
         return out
 
-    def fetch(self, prep: Prepared, out):
-        """Rank 0: (quartets u32[Q,4], rstat u32[Q,2], rscor f64[Q,3]) on the host; synchronises."""
-        if self.device is not None:
-            self.torch.cuda.synchronize(self.device)
-        if out is None:
-            return None
+    def _start_fetch(self, prep: Prepared, out):
+        """Rank 0: results -> pinned host buffers on the copy stream, behind this replicate's completion event only."""
+        torch = self.torch
+        slot = prep.idx % len(self.engines)
         rstat, rscor = out[0], out[1]
+        for name, t in (("rstat", rstat), ("rscor", rscor)):
+            key = (name, slot)
+            if key not in self._pinned or self._pinned[key].shape != t.shape or self._pinned[key].dtype != t.dtype:
+                self._pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(prep.done)
+            for name, t in (("rstat", rstat), ("rscor", rscor)):
+                self._pinned[(name, slot)].copy_(t, non_blocking=True)
+                prep.host[name] = self._pinned[(name, slot)]
+            prep.fetched = torch.cuda.Event()
+            prep.fetched.record(self.copy_stream)
+
+    def wait(self, prep: Prepared):
+        """Block the host until replicate ``prep`` (not the ones queued behind it) has finished on the device."""
+        if prep.done is not None:
+            prep.done.synchronize()
+
+    def fetch(self, prep: Prepared, out):
+        """Rank 0: (quartets u32[Q,4], rstat u32[Q,2], rscor f64[Q,3]) on the host.  Waits for THIS replicate's
+        results only; replicates already queued behind it keep the device busy meanwhile."""
+        if out is None:
+            self.wait(prep)
+            return None
+        if prep.fetched is not None:
+            prep.fetched.synchronize()
+            rstat = prep.host["rstat"].numpy().view(np.uint32).copy()        # the staging buffers are reused
+            rscor = prep.host["rscor"].numpy().copy()
+        else:
+            self.wait(prep)
+            rstat, rscor = out[0].cpu().numpy().view(np.uint32), out[1].cpu().numpy()
         if prep.quartets is None:
             if prep.q_event is not None:
                 prep.q_event.synchronize()
-                prep.quartets = prep.q_host_pinned.numpy().view(np.uint32).copy()    # the staging buffer is reused
+                prep.quartets = prep.q_host_pinned.numpy().view(np.uint32).copy()
             else:
                 prep.quartets = prep.q_dev.cpu().numpy().view(np.uint32)
-        return prep.quartets, rstat.cpu().numpy().view(np.uint32), rscor.cpu().numpy()
+        return prep.quartets, rstat, rscor
 
     def close(self):
         for eng in self.engines:

@@ -321,7 +321,8 @@ def agreed_seed(seed):
 
 
 def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int = 0, resolver=None,
-                  device_bootstrap: bool = True, overlap_sink: bool = True, save_invariants: bool = False) -> None:
+                  device_bootstrap: bool = True, overlap_sink: bool = True, save_invariants: bool = False,
+                  quartet_sampler: str | None = None) -> None:
     """Resolve replicate 0 (original data) and ``nboots`` bootstrap replicates, checkpointing
     after each one exactly like the reference (:405-407).  ``ncores`` is accepted for CLI
     compatibility and ignored: the work runs on the GPU(s).  ``resolver`` (tests) overrides the
@@ -332,6 +333,9 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
     ``save_invariants`` keeps every replicate's site-pattern count matrices, the deprecated API's option
     (deprecated/distributor.py:231-257 stores them as ``invariants/boot{k}`` u16[nquartets,16,16] in its HDF5):
     here ``{name}.invariants_{rep}.npy``, u32[nquartets,16,16] (= ``mats[0]``; u32 because counts pass 65 535).
+
+    ``quartet_sampler`` ("device" | "numpy", default: the project's, else "device"): how a random quartet sample
+    (``nquartets < C(n,4)``) is drawn, see ``replicate.py``.
 
     The GPU side of a replicate is ``replicate.ReplicatePipeline`` (draw -> prepare -> resolve -> fetch, two engines
     alternating): replicate r + 1 is drawn, planned and queued on the device while replicate r resolves, and the
@@ -353,7 +357,8 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
         rng = proj.bootstrap_rng.to_rng()
 
     pipe = ReplicatePipeline(arrays, proj.nsamples, proj.nqrts, proj.nqrts_total, proj.subsample_snps, device=device,
-                             seed=proj.random_seed or 0, resolver=resolver, device_bootstrap=device_bootstrap)
+                             seed=proj.random_seed or 0, resolver=resolver, device_bootstrap=device_bootstrap,
+                             sampler=quartet_sampler or getattr(proj, "quartet_sampler", None) or "device")
 
     from concurrent.futures import ThreadPoolExecutor
     # Two sink workers: the heavy part of a replicate's sink (TSV, wQMC input, wQMC itself) is independent of its
@@ -362,22 +367,23 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
     pool = ThreadPoolExecutor(max_workers=2) if overlap_sink else None
     pending = []
 
-    draws = prep = None
+    draws = prep = out = None
     if proj.bootstrap_idx <= nboots:
         draws = pipe.draw(proj.bootstrap_idx, rng)
         prep = pipe.prepare(draws)
+        out = pipe.resolve(prep, want_counts=save_invariants)          # asynchronous on the GPU
     while proj.bootstrap_idx <= nboots:
         t_start = time.perf_counter()
         idx = proj.bootstrap_idx
-        out = pipe.resolve(prep, want_counts=save_invariants)          # asynchronous on the GPU
         rng_state = draws["state"]                                     # generator state after this replicate's draws
-        # the next replicate: host draws and plan now, its device work queued behind this replicate's resolve
-        next_draws = next_prep = None
+        # the next replicate is drawn, planned, packed and resolved behind this one before this one's results are read
+        next_draws = next_prep = next_out = None
         if idx + 1 <= nboots:
             next_draws = pipe.draw(idx + 1, rng)
             next_prep = pipe.prepare(next_draws)
+            next_out = pipe.resolve(next_prep, want_counts=save_invariants)
         t_next = time.perf_counter()
-        got = pipe.fetch(prep, out)                                    # rank 0: results on the host (synchronises)
+        got = pipe.fetch(prep, out)                                    # rank 0: this replicate's results on the host
         t_gpu = time.perf_counter()
         while len(pending) >= 2:
             pending.pop(0).result()                        # at most two replicates' sinks in flight
@@ -398,7 +404,7 @@ def run_inference(proj: Project, ncores: int = 0, nboots: int = 0, device: int =
                     f"hand-off to sink {time.perf_counter() - t_gpu:.3f} s")
         proj.bootstrap_idx += 1
         proj.bootstrap_rng = rng_state
-        draws, prep = next_draws, next_prep
+        draws, prep, out = next_draws, next_prep, next_out
     for fut in pending:
         fut.result()
     if pool is not None:

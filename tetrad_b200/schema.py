@@ -34,6 +34,9 @@ class Project(BaseModel):
     weights: int = 0
     nquartets: int = 0
     random_seed: int | None = 0
+    # not a field of the reference (its loader ignores unknown keys): how random quartet samples are drawn,
+    # "device" (keyed permutation on the GPU, scales with the number of GPUs) or "numpy" (the reference's host draw)
+    quartet_sampler: str = "device"
     # checkpointing (schema.py:46-47)
     bootstrap_idx: int = 0
     bootstrap_rng: RNGStateModel | None = None
