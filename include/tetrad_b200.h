@@ -143,7 +143,8 @@ int tq_boot_pack_rows(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntip
  *   d_counts u32[m][256] or NULL = mats[0] row-major (index 64a+16b+4c+d),
  *   d_minrank u32[m] or NULL.
  * subsample != 0 -> one SNP per locus (subsample_chunk_to_matrices); 0 -> all SNPs
- * (full_chunk_to_matrices).  Tip indices must be < ntips (checked on the device: offending
+ * (full_chunk_to_matrices; a list that holds >= 30 % of all C(ntips,4) quartets goes through one u8 GEMM over tip
+ * pairs on tcgen05.mma, which needs the tips of a quartet in ascending order, as the reference produces them).  Tip indices must be < ntips (checked on the device: offending
  * quartets get best = 0xFFFFFFFF and the call's status word, if given, is set non-zero).
  */
 int tq_resolve(const tq_plan *plan, const uint32_t *d_planes, int64_t ntips,
@@ -214,11 +215,15 @@ int64_t tq_launch_count(void);
  * ("tq::resolve_mma_kernel<true>", ...); a static string, never NULL */
 const char *tq_last_kernel(void);
 
-/* Tuning / test hooks; process-wide, initialised from the environment (TQ_KERNEL, TQ_MMA_FLUSH).
- *   "kernel"           0 = chosen by launch size (default), 1 = fused one-warp-per-quartet POPC kernel,
- *                      2 = warp-specialised POPC kernel, 3 = tensor-core (IMMA) count kernel
+/* Tuning / test hooks; process-wide, initialised from the environment (TQ_KERNEL, TQ_MMA_FLUSH, TQ_SHARED_RING).
+ *   "kernel"           0 = chosen by launch size and mode (default), 1 = one-warp-per-quartet POPC kernel,
+ *                      3 = tensor-core (IMMA) count kernel with per-warp cp.async rings, 4 = the same with the CTA-shared
+ *                      ring of TMA bulk copies, 5 = tip-pair GEMM on tcgen05.mma (full mode; subsample launches run 4)
+ *   "shared_ring"      which staging the tensor-core count kernel uses when it is chosen by size: 1 (default) the
+ *                      CTA-shared TMA ring, 0 per-warp cp.async rings
  *   "mma_flush_every"  > 0: tile products between accumulator flushes of the tensor-core kernel
  *                      (default 16384; tests lower it to reach the flush path), 0 = default
+ *   "pairgemm_desc_mode"  debugging aid of the tip-pair GEMM's shared-memory descriptors (0 = as documented)
  * Returns TQ_EINVAL for an unknown name or an out-of-range value. */
 int tq_set_option(const char *name, int64_t value);
 

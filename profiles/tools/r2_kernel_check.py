@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Round-2 bring-up helper (GPU box): one phase per process, so that a trapped kernel cannot poison the next phase.
+
+    python profiles/tools/r2_kernel_check.py pairgemm <desc_mode>     small full-mode case through the tip-pair GEMM vs the oracle
+    python profiles/tools/r2_kernel_check.py time <config> <kernel> <sub|full> [reps]   one launch shape timed with CUDA events
+"""
+import sys
+import time
+from itertools import combinations
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+
+def pairgemm(desc_mode: int):
+    import torch
+    import tetrad_b200
+    from tetrad_b200 import _lib, synth
+    from oracle import oracle
+    lib = _lib.load()
+    _lib.check(lib.tq_set_option(b"pairgemm_desc_mode", desc_mode))
+    for n, nloci, nsnps in ((6, 50, 200), (14, 4000, 15000)):
+        d = synth.generate(n, nloci, nsnps, seed=5)
+        db = synth.prepare_database(d.snps, d.snpsmap, seed=5)
+        quartets = np.array(list(combinations(range(n), 4)), dtype=np.uint32)
+        eng = tetrad_b200.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+        _lib.set_kernel("pairgemm")
+        rstat, rscor, counts, minrank = eng.resolve(quartets, False, want_counts=True)
+        torch.cuda.synchronize()
+        _, ostat, oscor, det = oracle.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], quartets, False, return_details=True)
+        got = counts.cpu().numpy().view(np.uint32).reshape(-1, 16, 16)
+        want = det["mats"][:, 0]
+        ok = (got == want).all()
+        print(f"desc_mode {desc_mode} n={n}: counts {'MATCH' if ok else 'DIFFER'}; kernel {lib.tq_last_kernel().decode()}")
+        if not ok:
+            bad = np.argwhere(got != want)
+            print("  first mismatches (quartet, ab, cd):", bad[:6].tolist())
+            q = bad[0][0]
+            print("  got row sums", got[q].sum(1).tolist(), "\n  want row sums", want[q].sum(1).tolist())
+            print("  got total", int(got[q].sum()), "want total", int(want[q].sum()))
+        else:
+            print("  nsnps equal:", bool((rstat.cpu().numpy().view(np.uint32) == ostat).all()),
+                  " max score err:", float(np.abs(rscor.cpu().numpy() - oscor).max()))
+
+
+def timed(config: str, kernel: str, mode: str, reps: int = 5):
+    import torch
+    import tetrad_b200
+    from tetrad_b200 import _lib, synth, combinations as cb
+    lib = _lib.load()
+    db = synth.config_arrays(config)
+    cfg = synth.CONFIGS[config]
+    n = cfg["ntips"]
+    if cfg["nquartets"] == 0:
+        q = cb.device_quartets(n)
+    else:
+        q = cb.device_sample(n, 7, cfg["nquartets"])
+    eng = tetrad_b200.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+    _lib.set_kernel(kernel)
+    sub = mode == "sub"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    times = []
+    for i in range(reps + 2):
+        flush.fill_(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rstat, rscor = eng.resolve(q, sub)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
+    print(f"{config} {mode} {kernel}: {ms:.3f} ms  {len(q) / ms / 1e3:.3f} M quartets/s  [{lib.tq_last_kernel().decode()}]  "
+          f"checksum {int(rstat.to(torch.int64).sum())} {float(rscor.sum()):.6f}")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "pairgemm":
+        pairgemm(int(sys.argv[2]))
+    else:
+        timed(sys.argv[2], sys.argv[3], sys.argv[4], int(sys.argv[5]) if len(sys.argv) > 5 else 5)

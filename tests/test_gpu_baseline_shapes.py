@@ -63,7 +63,7 @@ def check_against_oracle(eng, oracle, db, quartets, sub, label):
     return worst
 
 
-@pytest.mark.parametrize("kernel_name", ["fused", "ws", "mma"])
+@pytest.mark.parametrize("kernel_name", ["fused", "mma", "mma_shared", "pairgemm"])
 @pytest.mark.parametrize("sub", [True, False])
 def test_c1_exhaustive(tb, oracle, kernel_name, sub):
     """C1: 12 tips, 5 000 loci, 20 000 SNPs, all 495 quartets -- the reference's own CPU-runnable case."""
@@ -87,9 +87,10 @@ def test_c2_sampled(tb, oracle, sub):
     db = config("C2")
     quartets = sampled_quartets("C2", 2000)
     eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
-    _lib.set_kernel("mma")
     try:
-        check_against_oracle(eng, oracle, db, quartets, sub, f"C2_{'sub' if sub else 'full'}_mma")
+        for name in ("mma", "mma_shared"):
+            _lib.set_kernel(name)
+            check_against_oracle(eng, oracle, db, quartets, sub, f"C2_{'sub' if sub else 'full'}_{name}")
     finally:
         _lib.set_kernel("auto")
         eng.close()
@@ -103,6 +104,8 @@ def test_c2_full_mode_whole_list_default_kernel(tb, oracle):
     eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
     quartets = cb.device_quartets(50)
     rstat, rscor, counts, minrank = eng.resolve(quartets, False, want_counts=True)
+    from tetrad_b200 import _lib
+    assert "pair_gemm_kernel" in _lib.load().tq_last_kernel().decode()      # an exhaustive list: the tcgen05 tip-pair GEMM
     pick = np.linspace(0, len(quartets) - 1, 600).astype(np.int64)
     qh = quartets.cpu().numpy().view(np.uint32)[pick]
     _, ostat, oscor, det = oracle.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], qh, False, return_details=True)
@@ -123,10 +126,10 @@ def test_large_shapes_sampled(tb, oracle, name, count, modes):
     db = config(name)
     quartets = sampled_quartets(name, count)
     eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
-    _lib.set_kernel("mma")
+    _lib.set_kernel("mma_shared")
     try:
         for sub in modes:
-            check_against_oracle(eng, oracle, db, quartets, sub, f"{name}_{'sub' if sub else 'full'}_mma")
+            check_against_oracle(eng, oracle, db, quartets, sub, f"{name}_{'sub' if sub else 'full'}_mma_shared")
     finally:
         _lib.set_kernel("auto")
         eng.close()

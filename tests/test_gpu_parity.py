@@ -18,11 +18,12 @@ def tb():
     return tetrad_b200
 
 
-@pytest.fixture(params=["fused", "ws", "mma"])
+@pytest.fixture(params=["fused", "mma", "mma_shared"])
 def kernel(request, tb):
-    """Every resolve-kernel variant behind launch_resolve (tq_kernels.cu): the fused one-warp-per-quartet POPC
-    kernel, the warp-specialised POPC kernel and the tensor-core (IMMA) count kernel.  The default rule picks by
-    launch size, so small test launches would otherwise only ever see the fused kernel."""
+    """Every resolve-kernel variant behind launch_resolve (tq_resolve.cu): the fused one-warp-per-quartet POPC kernel
+    and the tensor-core (IMMA) count kernel with its two ways of staging the tip rows (per-warp cp.async rings, one
+    CTA-shared ring of TMA bulk copies).  The default rule picks by launch size, so small test launches would otherwise
+    only ever see the fused kernel.  (Full mode has a fourth: the tip-pair GEMM, test_pairgemm_* below.)"""
     from tetrad_b200 import _lib
     _lib.set_kernel(request.param)
     yield request.param
@@ -99,7 +100,7 @@ def test_seeded_vs_oracle(tb, oracle, kernel, shape, sub):
     assert_best_matches(rstat[:, 0], oscor, ostat)
     has = ostat[:, 1] > 0
     assert (extra["minrank"][has] == det["minrank"][has]).all()
-    assert {"fused": "resolve_kernel", "ws": "resolve_ws_kernel", "mma": "resolve_mma_kernel"}[kernel] in last_kernel()
+    assert {"fused": "resolve_kernel", "mma": "cp.async rings", "mma_shared": "shared TMA ring"}[kernel] in last_kernel()
 
 
 def test_bootstrap_replicate_vs_oracle(tb, oracle):
@@ -341,7 +342,7 @@ def test_kernel_variants_agree_bit_for_bit(tb, sub):
     eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
     outs = []
     try:
-        for name in ("fused", "ws", "mma", "mma"):
+        for name in ("fused", "mma", "mma_shared", "mma_shared") + (() if sub else ("pairgemm",)):
             _lib.set_kernel(name)
             rstat, rscor, counts, minrank = eng.resolve(quartets, sub, want_counts=True)
             outs.append((rstat.cpu().numpy().copy(), rscor.cpu().numpy().copy(), counts.cpu().numpy().copy(),
@@ -370,3 +371,49 @@ def test_results_do_not_depend_on_order_or_batching(tb):
     for lo, hi in ((0, 7001), (7001, 20000)):                     # two launches of other sizes
         hstat, hscor = eng.resolve(np.ascontiguousarray(quartets[lo:hi]), True)
         assert (hstat.cpu().numpy() == rstat[lo:hi]).all() and (hscor.cpu().numpy() == rscor[lo:hi]).all()
+
+
+def test_pairgemm_full_mode_small_and_ragged(tb, oracle):
+    """The tip-pair GEMM (tcgen05.mma kind::i8) forced on small shapes: fewer pairs than one tile holds, a tile grid with
+    ragged edges, an out-of-range quartet, a duplicate quartet and an empty chunk of the list -- exact counts, nsnps,
+    minrank and the same score bits as the per-quartet kernel."""
+    from itertools import combinations
+    from tetrad_b200 import _lib, synth
+    for n, nloci, nsnps in ((5, 40, 160), (9, 700, 2600), (21, 1500, 5000)):
+        d = synth.generate(n, nloci, nsnps, seed=200 + n)
+        db = synth.prepare_database(d.snps, d.snpsmap, seed=n)
+        quartets = np.array(list(combinations(range(n), 4)), dtype=np.uint32)
+        if len(quartets) > 1500:
+            quartets = quartets[np.sort(np.random.default_rng(2).choice(len(quartets), 1500, replace=False))]
+        quartets = np.vstack([quartets, quartets[:1]])                 # a duplicate
+        eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+        try:
+            _lib.set_kernel("pairgemm")
+            rstat, rscor, counts, minrank = eng.resolve(quartets, False, want_counts=True)
+            assert "pair_gemm_kernel" in last_kernel()
+            eng.check_status()
+            _lib.set_kernel("mma")
+            mstat, mscor, mcounts, mminrank = eng.resolve(quartets, False, want_counts=True)
+        finally:
+            _lib.set_kernel("auto")
+        _, ostat, oscor, det = oracle.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], quartets, False, return_details=True)
+        got = counts.cpu().numpy().view(np.uint32).reshape(-1, 16, 16)
+        assert (got == det["mats"][:, 0]).all(), "tip-pair GEMM counts differ from the oracle"
+        assert (rstat.cpu().numpy().view(np.uint32) == ostat).all()
+        assert (counts == mcounts).all() and (rstat == mstat).all() and (minrank == mminrank).all()
+        assert rscor.cpu().numpy().tobytes() == mscor.cpu().numpy().tobytes()
+        assert_scores_close(rscor.cpu().numpy(), oscor, ostat[:, 1], counts=got)
+        # a quartet with a tip out of range is flagged, the others are unaffected
+        bad = quartets[:40].copy()
+        bad[7, 3] = n + 3
+        try:
+            _lib.set_kernel("pairgemm")
+            bstat, bscor = eng.resolve(bad, False)
+            with pytest.raises(IndexError):
+                eng.check_status()
+        finally:
+            _lib.set_kernel("auto")
+        keep = np.arange(40) != 7
+        assert (bstat.cpu().numpy().view(np.uint32)[keep] == ostat[:40][keep]).all()
+        assert bstat.cpu().numpy().view(np.uint32)[7, 0] == 0xFFFFFFFF
+        eng.close()

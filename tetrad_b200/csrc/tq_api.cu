@@ -131,8 +131,19 @@ int tq_set_option(const char *name, int64_t value)
 {
     if (!name) return fail(TQ_EINVAL, "tq_set_option: null name");
     if (!strcmp(name, "kernel")) {
-        if (value < 0 || value > 3) return fail(TQ_EINVAL, "tq_set_option: kernel must be 0 (auto), 1 (fused), 2 (ws) or 3 (mma)");
+        if (value < 0 || value > 5 || value == 2)
+            return fail(TQ_EINVAL, "tq_set_option: kernel must be 0 (auto), 1 (fused), 3 (mma), 4 (mma_shared) or 5 (pairgemm)");
         tq::g_kernel_choice = (int)value;
+        return TQ_OK;
+    }
+    if (!strcmp(name, "shared_ring")) {
+        if (value < 0 || value > 1) return fail(TQ_EINVAL, "tq_set_option: shared_ring must be 0 or 1");
+        tq::g_default_shared_ring = (int)value;
+        return TQ_OK;
+    }
+    if (!strcmp(name, "pairgemm_desc_mode")) {
+        if (value < 0 || value > 1) return fail(TQ_EINVAL, "tq_set_option: pairgemm_desc_mode must be 0 or 1");
+        tq::g_pairgemm_desc_mode = (int)value;
         return TQ_OK;
     }
     if (!strcmp(name, "mma_flush_every")) {

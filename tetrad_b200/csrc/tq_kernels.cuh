@@ -38,6 +38,12 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
                            uint32_t *d_minrank, uint32_t *d_status, int num_sms,
                            cudaStream_t stream);
 
+// full mode over tip pairs on tcgen05 (tq_pairgemm.cu): whether a launch of m quartets of ntips tips is dense enough for it
+bool pairgemm_applies(int64_t ntips, int64_t m, int num_sms);
+cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips, const uint32_t *d_quartets,
+                                    int64_t m, uint64_t seed, double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
+                                    uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream);
+
 cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint32_t ntips, uint32_t *d_quartets,
                           cudaStream_t stream);
 
@@ -49,7 +55,10 @@ void sample_ranks_host(int64_t start, int64_t m, uint32_t ntips, uint64_t key, i
 cudaError_t run_microbench(int kind, double *result);
 
 extern std::atomic<int64_t> g_launches;      // kernels launched by this library since load
-extern std::atomic<int> g_kernel_choice;          // 0 by launch size, 1 fused, 2 warp-specialised POPC, 3 tensor-core count
+extern std::atomic<int> g_kernel_choice;          // 0 by launch size, 1 fused POPC, 3 tensor-core count (cp.async rings),
+                                                  // 4 tensor-core count (CTA-shared TMA ring), 5 tip-pair GEMM (full mode)
+extern std::atomic<int> g_default_shared_ring;    // staging of the tensor-core count kernel when chosen by size: 1 shared TMA ring
+extern std::atomic<int> g_pairgemm_desc_mode;     // debugging: 1 swaps the descriptor offsets of the tip-pair GEMM
 extern std::atomic<int64_t> g_mma_flush;          // > 0: tile products between accumulator flushes of the tensor-core kernel (tests)
 extern std::atomic<const char *> g_last_kernel;   // name of the resolve kernel variant launched last
 

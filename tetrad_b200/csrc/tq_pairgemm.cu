@@ -1,0 +1,492 @@
+// Full mode (subsample_snps = False, the reference CLI's default: tetrad/src/cli_init.py:61) for dense quartet lists as
+// ONE u8 GEMM over tip PAIRS on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in tensor memory).
+//
+// full_chunk_to_matrices (tetrad/src/resolve_quartets.py:76-104) counts EVERY column whose four cells are bases:
+//
+//     T_q[ab][cd] = sum over columns s of  X^{(t0,t1)}_{ab}[s] * Y^{(t2,t3)}_{cd}[s],     X_ab = A_a(t0) & B_b(t1),
+//                                                                                          Y_cd = C_c(t2) & D_d(t3)
+//
+// (a missing cell has no plane bit, so incomplete columns drop out by themselves; the four invariant patterns aaaa are
+// zeroed afterwards, :88-95 / :218).  Unlike subsample mode there is no per-locus selection, so the operands depend on
+// a tip PAIR only: all quartets that share (t0, t1) share X, all that share (t2, t3) share Y, and the counts of every
+// quartet are 16 x 16 blocks of the product of the pair-plane matrix with itself.  The per-quartet tensor-core kernel
+// (tq_resolve.cu) unpacks both operands once per QUARTET (206 tile products of 16 x 16 x 1024 at the C2 shape); here
+// they are unpacked once per PAIR and tile:
+//
+//   tile        8 row pairs (t0 < t1) x 16 column pairs (t2 < t3) = 128 x 256 outputs = 128 candidate quartets;
+//               pairs are numbered by (t1, t0) and by (t2, t3), so the tiles that hold wanted quartets (t1 < t2) form a
+//               staircase -- a device planner buckets the quartet list by tile, and only non-empty tiles are computed
+//   K           all 32-column words of the packed rows; one tcgen05.mma (M = 128, N = 256, K = 32 bytes) per word
+//   producers   12 warps, thread = one operand row (pair, ab): two 4-byte plane loads, one AND, and the 32 columns of
+//               the word become 32 bytes {0, 1} -- (x >> v) & 0x01010101 for v = 0..7 -- written as two 16-byte K chunks
+//               into the stage's K-major core-matrix layout (no swizzle: 8 rows x 16 B = one 128-byte core matrix)
+//   MMA         one thread issues 4 MMAs per stage (kKW = 4 words), tcgen05.commit releases the stage / publishes the tile
+//   epilogue    4 warps (one per tensor-memory lane quadrant) read the wanted 16 x 16 blocks with tcgen05.ld and write the
+//               quartet's 256 counts (1 KB) to global memory; two accumulator buffers (2 x 256 TMEM columns) overlap the
+//               epilogue of tile i with the main loop of tile i + 1
+//   scores      score_counts_kernel (the same svd_scores4 as every other kernel) on a second stream, one group of tiles
+//               behind the GEMM: its CTAs (6 warps, FP64) fit beside a GEMM CTA on the SM
+//
+// Exactness: products are 0/1, accumulation is s32, K < 2^31 columns: counts are exact integers, bit-identical to the
+// other kernels'.  Applies when the list holds >= 30 % of all C(n,4) quartets (exhaustive lists in practice; a sparse
+// random sample would compute 128 candidates to use one or two -- the per-quartet kernel keeps those).
+#include "tq_kernels.cuh"
+#include "tq_device.cuh"
+#include "tq_svd.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+#include <mutex>
+
+namespace tq {
+
+static constexpr unsigned kFull = 0xFFFFFFFFu;
+static constexpr int kRP = 8;                     // row pairs per tile    -> M = 128
+static constexpr int kCP = 16;                    // column pairs per tile -> N = 256
+static constexpr int kKW = 4;                     // plane words per stage -> 4 MMAs of K = 32 bytes
+static constexpr int kGStages = 3;
+static constexpr int kProdWarps = 12;             // 384 producer threads = 128 A rows + 256 B rows
+static constexpr int kMmaWarp = kProdWarps;       // warp 12
+                                                  // warps 13..16: epilogue (their index % 4 covers the four TMEM lane quadrants)
+static constexpr int kGemmThreads = (kProdWarps + 5) * 32;
+static constexpr uint32_t kABytes = kKW * 2 * 128 * 16;      // 16 KB: [word][K chunk][row][16 B]
+static constexpr uint32_t kBBytes = kKW * 2 * 256 * 16;      // 32 KB
+static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+static constexpr uint32_t kTmemColsGemm = 512;               // two accumulators of 256 columns
+static constexpr int kScoreWarps = 6;
+static constexpr int kGroups = 4;                            // tile groups: scores of group g run beside the GEMM of group g + 1
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 at bit 4, a/b_format U8 = 0, K-major both,
+// n_dim = N >> 3 at bit 17, m_dim = M >> 4 at bit 24
+static constexpr uint32_t kIdesc = (2u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, no swizzle: start address >> 4, leading byte
+// offset (between the two K chunks of a K = 32 step) >> 4 at bit 16, stride byte offset (between 8-row groups) >> 4 at
+// bit 32, version 1 at bit 46, layout type 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+struct PairGemmArgs {
+    const uint32_t *planes;        // u32 view of the packed planes: word w of tip t, base x at ((t * row_u4 + w) * 4 + x)
+    uint32_t row_u4;
+    uint32_t ntips;
+    uint32_t npairs;               // n (n - 1) / 2
+    uint32_t ntc;                  // column tiles per tile row
+    const uint32_t *tile_list;     // non-empty cells, ascending
+    const uint32_t *tile_range;    // [kGroups + 1] tile index boundaries of the groups
+    const uint32_t *cell_off;      // first entry of every cell
+    const uint32_t *cell_count;
+    const uint2 *entries;          // (quartet index, local row pair << 8 | local column pair), bucketed by cell
+    uint32_t *counts;              // [m][256]
+    uint32_t desc_mode;            // debugging: 1 swaps the two descriptor offsets
+};
+
+// pair numbering: row pairs by (t1, t0): rp = t1 (t1 - 1) / 2 + t0;  column pairs by (t2, t3): cp = off(t2) + t3 - t2 - 1
+__host__ __device__ __forceinline__ uint32_t rowpair_index(uint32_t t0, uint32_t t1) { return t1 * (t1 - 1) / 2 + t0; }
+__host__ __device__ __forceinline__ uint32_t colpair_offset(uint32_t t2, uint32_t n) { return t2 * (2 * n - 1 - t2) / 2; }
+__host__ __device__ __forceinline__ uint32_t colpair_index(uint32_t t2, uint32_t t3, uint32_t n) { return colpair_offset(t2, n) + t3 - t2 - 1; }
+
+__device__ __forceinline__ uint2 unrank_rowpair(uint32_t rp)
+{
+    uint32_t t1 = (uint32_t)((1.0 + sqrt(1.0 + 8.0 * (double)rp)) * 0.5);
+    while (t1 * (t1 - 1) / 2 > rp) --t1;
+    while (t1 * (t1 + 1) / 2 <= rp) ++t1;
+    return make_uint2(rp - t1 * (t1 - 1) / 2, t1);
+}
+__device__ __forceinline__ uint2 unrank_colpair(uint32_t cp, uint32_t n)
+{
+    uint32_t lo = 0, hi = n - 2;                     // largest t2 with off(t2) <= cp
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (colpair_offset(mid, n) <= cp) lo = mid; else hi = mid - 1;
+    }
+    return make_uint2(lo, lo + 1 + (cp - colpair_offset(lo, n)));
+}
+
+// ------------------------------------------------------------------------------------------
+// planner: bucket the quartets by tile
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool quartet_cell(uint4 t, uint32_t n, uint32_t ntc, uint32_t &cell, uint32_t &local)
+{
+    if (!(t.x < t.y && t.y < t.z && t.z < t.w && t.w < n)) return false;
+    const uint32_t rp = rowpair_index(t.x, t.y), cp = colpair_index(t.z, t.w, n);
+    cell = (rp / kRP) * ntc + cp / kCP;
+    local = ((rp % kRP) << 8) | (cp % kCP);
+    return true;
+}
+
+// quartets whose tips are out of range (or not ascending) never reach a tile: they get the error marks here
+__global__ void __launch_bounds__(256) pg_count_kernel(const uint4 *__restrict__ quartets, int64_t m, uint32_t n, uint32_t ntc,
+                                                       uint32_t *__restrict__ cell_count, double *__restrict__ rscor,
+                                                       uint2 *__restrict__ rstat, uint32_t *__restrict__ status)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    uint32_t cell, local;
+    if (quartet_cell(__ldg(quartets + q), n, ntc, cell, local)) {
+        atomicAdd(cell_count + cell, 1u);
+    } else {
+        rstat[q] = make_uint2(0xFFFFFFFFu, 0u);
+        rscor[3 * q] = rscor[3 * q + 1] = rscor[3 * q + 2] = 0.0;
+        if (status) atomicOr(status, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) pg_flag_kernel(const uint32_t *__restrict__ cell_count, uint32_t ncells, uint32_t *__restrict__ flag)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncells) flag[i] = cell_count[i] != 0u;
+}
+
+// tile_list[flag_scan[cell]] = cell for every non-empty cell (ascending), then the group boundaries
+__global__ void __launch_bounds__(256) pg_compact_kernel(const uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ flag_scan,
+                                                         uint32_t ncells, uint32_t grid, uint32_t *__restrict__ tile_list,
+                                                         uint32_t *__restrict__ tile_range)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncells && cell_count[i] != 0u) tile_list[flag_scan[i]] = i;
+    if (i == 0) {
+        // every tile costs the same, so a group is a whole number of waves of `grid` CTAs; the last one takes the rest
+        const uint32_t nact = flag_scan[ncells];
+        const uint32_t waves = (nact + grid - 1) / grid, per = (waves + kGroups - 1) / kGroups;
+        for (int g = 0; g <= kGroups; ++g) tile_range[g] = min(nact, (uint32_t)g * per * grid);
+        tile_range[kGroups] = nact;
+    }
+}
+
+__global__ void __launch_bounds__(256) pg_fill_kernel(const uint4 *__restrict__ quartets, int64_t m, uint32_t n, uint32_t ntc,
+                                                      const uint32_t *__restrict__ cell_off, uint32_t *__restrict__ cell_fill,
+                                                      uint2 *__restrict__ entries)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    uint32_t cell, local;
+    if (!quartet_cell(__ldg(quartets + q), n, ntc, cell, local)) return;
+    const uint32_t pos = cell_off[cell] + atomicAdd(cell_fill + cell, 1u);
+    entries[pos] = make_uint2((uint32_t)q, local);
+}
+
+// ------------------------------------------------------------------------------------------
+// the GEMM
+// ------------------------------------------------------------------------------------------
+struct __align__(16) PairGemmShared {
+    unsigned long long full[kGStages], empty[kGStages];     // stage filled by the producers / released by the MMAs
+    unsigned long long tfull[2], tempty[2];                 // accumulator published / drained
+    uint32_t tmem_base;
+};
+
+// (72 registers: a score CTA of 6 x 32 threads x 128 registers fits beside the 544 threads of this one)
+__global__ void __maxnreg__(72)
+pair_gemm_kernel(PairGemmArgs args, int group)
+{
+    extern __shared__ __align__(1024) unsigned char pg_smem[];
+    unsigned char *stages = pg_smem;
+    PairGemmShared &sh = *reinterpret_cast<PairGemmShared *>(pg_smem + kGStages * kStageBytes);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGStages; ++s) { mbar_init(&sh.full[s], kProdWarps); mbar_init(&sh.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sh.tfull[b], 1); mbar_init(&sh.tempty[b], 4); }
+        mbar_init_fence();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&sh.tmem_base, kTmemColsGemm);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = sh.tmem_base;
+
+    const uint32_t tile_lo = args.tile_range[group], tile_hi = args.tile_range[group + 1];
+    const uint32_t nst = args.row_u4 / kKW;                  // stages per tile (row_u4 is a multiple of 32)
+    const uint32_t stage0 = smem_u32(stages);
+
+    if (warp < kProdWarps) {
+        // ------------------------------ producers: bits -> bytes ------------------------------
+        const uint32_t row = threadIdx.x;                    // 0..127: A rows, 128..383: B rows
+        const bool is_a = row < 128u;
+        const uint32_t r = is_a ? row : row - 128u;          // row inside its operand
+        const uint32_t nrows = is_a ? 128u : 256u;
+        const uint32_t dst0 = (is_a ? 0u : kABytes) + r * 16u;          // + word * nrows * 32 + chunk * nrows * 16
+        uint32_t it = 0;                                      // stages produced so far (ring position)
+        for (uint32_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
+            const uint32_t cell = __ldg(args.tile_list + tile);
+            const uint32_t tr = cell / args.ntc, tc = cell % args.ntc;
+            uint2 pr;                                        // my pair: (tip of the first plane, tip of the second plane)
+            if (is_a) { const uint32_t rp = tr * kRP + (r >> 4); pr = unrank_rowpair(rp < args.npairs ? rp : args.npairs - 1); }
+            else { const uint32_t cp = tc * kCP + (r >> 4); pr = unrank_colpair(cp < args.npairs ? cp : args.npairs - 1, args.ntips); }
+            const uint32_t *p0 = args.planes + (size_t)pr.x * args.row_u4 * 4 + ((r >> 2) & 3u);
+            const uint32_t *p1 = args.planes + (size_t)pr.y * args.row_u4 * 4 + (r & 3u);
+            uint32_t nx[kKW];                                 // the stage after the one being expanded, already loaded
+#pragma unroll
+            for (int w = 0; w < kKW; ++w) nx[w] = __ldg(p0 + 4 * w) & __ldg(p1 + 4 * w);
+            for (uint32_t st = 0; st < nst; ++st, ++it) {
+                uint32_t x[kKW];
+#pragma unroll
+                for (int w = 0; w < kKW; ++w) x[w] = nx[w];
+                if (st + 1 < nst) {
+#pragma unroll
+                    for (int w = 0; w < kKW; ++w) {
+                        const size_t o = ((size_t)(st + 1) * kKW + w) * 4;
+                        nx[w] = __ldg(p0 + o) & __ldg(p1 + o);
+                    }
+                }
+                const uint32_t s = it % kGStages;
+                mbar_wait_short(&sh.empty[s], ((it / kGStages) & 1u) ^ 1u);      // the MMAs that read this slot are done
+                const uint32_t base = stage0 + s * kStageBytes + dst0;
+#pragma unroll
+                for (int w = 0; w < kKW; ++w) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) o[v] = (x[w] >> v) & 0x01010101u;   // byte j of o[v] = column 8 j + v of the word
+                    const uint32_t a0 = base + (uint32_t)w * nrows * 32u;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a0 + nrows * 16u), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                }
+                fence_proxy_async_smem();                    // my stores are visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.full[s]);
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------ MMA issuer ------------------------------
+        const uint32_t a_lbo = args.desc_mode ? 128u : 128u * 16u, a_sbo = args.desc_mode ? 128u * 16u : 128u;
+        const uint32_t b_lbo = args.desc_mode ? 128u : 256u * 16u, b_sbo = args.desc_mode ? 256u * 16u : 128u;
+        uint32_t it = 0, tcount = 0;
+        for (uint32_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x, ++tcount) {
+            const uint32_t buf = tcount & 1u;
+            mbar_wait(&sh.tempty[buf], ((tcount >> 1) & 1u) ^ 1u);              // the epilogue has drained this accumulator
+            tcgen05_fence_after();
+            for (uint32_t st = 0; st < nst; ++st, ++it) {
+                const uint32_t s = it % kGStages;
+                mbar_wait_short(&sh.full[s], (it / kGStages) & 1u);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = stage0 + s * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+                    for (int w = 0; w < kKW; ++w)
+                        umma_i8(tmem_base + buf * 256u, make_desc(sa + (uint32_t)w * 128u * 32u, a_lbo, a_sbo),
+                                make_desc(sb + (uint32_t)w * 256u * 32u, b_lbo, b_sbo), kIdesc, (st | (uint32_t)w) != 0u);
+                    umma_commit(&sh.empty[s]);                // slot free once these MMAs have read it
+                    if (st + 1 == nst) umma_commit(&sh.tfull[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------ epilogue: TMEM -> counts ------------------------------
+        const uint32_t quad = (uint32_t)warp & 3u;
+        uint32_t tcount = 0;
+        for (uint32_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x, ++tcount) {
+            const uint32_t buf = tcount & 1u;
+            const uint32_t cell = __ldg(args.tile_list + tile);
+            const uint32_t e_lo = __ldg(args.cell_off + cell), e_hi = e_lo + __ldg(args.cell_count + cell);
+            mbar_wait(&sh.tfull[buf], (tcount >> 1) & 1u);
+            tcgen05_fence_after();
+            for (uint32_t e = e_lo; e < e_hi; ++e) {
+                const uint2 ent = __ldg(args.entries + e);
+                const uint32_t lr = ent.y >> 8, lc = ent.y & 0xFFu;
+                if ((lr >> 1) != quad) continue;              // rows 16 lr .. 16 lr + 15 live in lane quadrant lr / 2
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((quad * 32u) << 16) + buf * 256u + lc * 16u, v);
+                tmem_wait_ld();
+                if ((uint32_t)(lane >> 4) == (lr & 1u)) {
+                    const uint32_t ab = (uint32_t)lane & 15u;
+                    uint4 *dst = reinterpret_cast<uint4 *>(args.counts + (size_t)ent.x * 256 + ab * 16);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if ((uint32_t)k == ab && ab % 5u == 0u) v[k] = 0u;       // invariant patterns aaaa (ab = cd = 5 a), :218
+                    dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                    dst[2] = make_uint4(v[8], v[9], v[10], v[11]);
+                    dst[3] = make_uint4(v[12], v[13], v[14], v[15]);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.tempty[buf]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemColsGemm);
+}
+
+// ------------------------------------------------------------------------------------------
+// scores from finished count tensors (global memory), the quartets named by a range of planner entries
+// ------------------------------------------------------------------------------------------
+__global__ void __maxnreg__(128)
+score_counts_kernel(const uint32_t *__restrict__ counts, const uint4 *__restrict__ quartets, const uint2 *__restrict__ entries,
+                    const uint32_t *__restrict__ tile_list, const uint32_t *__restrict__ tile_range,
+                    const uint32_t *__restrict__ cell_off, const uint32_t *__restrict__ cell_count, int group, uint64_t seed,
+                    double *__restrict__ rscor, uint2 *__restrict__ rstat, uint32_t *__restrict__ minrank_out)
+{
+    extern __shared__ __align__(1024) unsigned char pg_smem[];
+    SvdScratch4 *scratch = reinterpret_cast<SvdScratch4 *>(pg_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SvdScratch4 &sv = scratch[warp];
+    const uint32_t tlo = tile_range[group], thi = tile_range[group + 1];
+    if (tlo >= thi) return;
+    const uint32_t last = __ldg(tile_list + thi - 1);
+    const uint32_t e_lo = __ldg(cell_off + __ldg(tile_list + tlo)), e_hi = __ldg(cell_off + last) + __ldg(cell_count + last);
+    const uint32_t nwarps = gridDim.x * kScoreWarps;
+    for (uint32_t base = e_lo + 4u * (blockIdx.x * kScoreWarps + warp); base < e_hi; base += 4u * nwarps) {
+        const int nq = (int)min(4u, e_hi - base);
+        uint32_t actmask = 0u, my_nsnps = 0u, my_best = 0u;
+        long long my_q = -1;
+        uint32_t qx[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nq) continue;
+            const uint32_t q = __ldg(entries + base + j).x;
+            const uint32_t *T = counts + (size_t)q * 256;
+            qx[j] = q;
+            uint32_t nsnps = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) nsnps += T[lane + 32 * i];
+            nsnps = __reduce_add_sync(kFull, nsnps);                        // :226
+            uint32_t best = 0;
+            if (nsnps == 0) best = tiebreak_split(seed, __ldg(quartets + q));   // stands in for :231
+            else actmask |= 1u << j;
+            if (lane == j) { my_q = q; my_nsnps = nsnps; my_best = best; }
+        }
+        double score[3] = {0.001, 0.001, 0.001};                            // :232
+        uint32_t minrank = 0;
+        if (actmask) {
+            const uint32_t q0 = qx[0], q1 = qx[1], q2 = qx[2], q3 = qx[3];
+            svd_scores4_impl([=](int qi) { return counts + (size_t)(qi == 0 ? q0 : qi == 1 ? q1 : qi == 2 ? q2 : q3) * 256; },
+                             actmask, sv, lane, score, my_best, minrank);
+        }
+        if (lane < 4 && my_q >= 0) {
+            rscor[3 * my_q] = score[0]; rscor[3 * my_q + 1] = score[1]; rscor[3 * my_q + 2] = score[2];
+            rstat[my_q] = make_uint2(my_best, my_nsnps);                    // :251, :264
+            if (minrank_out) minrank_out[my_q] = minrank;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+std::atomic<int> g_pairgemm_desc_mode{0};
+
+bool pairgemm_applies(int64_t ntips, int64_t m, int num_sms)
+{
+    if (ntips < 5 || ntips > 2048 || m < (int64_t)num_sms * 16) return false;
+    const double n = (double)ntips, total = n * (n - 1) * (n - 2) * (n - 3) / 24.0;
+    const uint64_t np = (uint64_t)ntips * (ntips - 1) / 2;
+    const uint64_t ncells = ((np + kRP - 1) / kRP) * ((np + kCP - 1) / kCP);
+    return (double)m >= 0.30 * total && ncells <= (4u << 20);
+}
+
+namespace {
+struct SideStream {             // one per device: the stream the scores run on beside the GEMM, and its events
+    std::mutex mu;
+    cudaStream_t stream[64] = {};
+    cudaError_t get(int dev, cudaStream_t *out)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!stream[dev & 63]) {
+            cudaError_t e = cudaStreamCreateWithFlags(&stream[dev & 63], cudaStreamNonBlocking);
+            if (e != cudaSuccess) return e;
+        }
+        *out = stream[dev & 63];
+        return cudaSuccess;
+    }
+};
+SideStream g_side;
+std::mutex g_attr_mu;
+uint64_t g_attr_done = 0;
+}  // namespace
+
+#define PG_CHECK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { if (scratch) cudaFreeAsync(scratch, stream); return e__; } } while (0)
+
+cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips, const uint32_t *d_quartets,
+                                    int64_t m, uint64_t seed, double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
+                                    uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream)
+{
+    if (m == 0) return cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t gemm_smem = (size_t)kGStages * kStageBytes + sizeof(PairGemmShared);
+    const size_t score_smem = sizeof(SvdScratch4) * kScoreWarps;
+    {
+        std::lock_guard<std::mutex> lk(g_attr_mu);
+        const uint64_t bit = 1ull << (dev & 63);
+        if (!(g_attr_done & bit)) {
+            cudaError_t e = cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(score_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score_smem);
+            if (e != cudaSuccess) return e;
+            g_attr_done |= bit;
+        }
+    }
+    cudaStream_t side = nullptr;
+    cudaError_t e0 = g_side.get(dev, &side);
+    if (e0 != cudaSuccess) return e0;
+
+    const uint32_t n = (uint32_t)ntips, np = n * (n - 1) / 2;
+    const uint32_t ntr = (np + kRP - 1) / kRP, ntc = (np + kCP - 1) / kCP, ncells = ntr * ntc;
+    // Quartet chunks: 1 KB of counts per quartet lives in scratch unless the caller wants the counts anyway.
+    const int64_t chunk_cap = d_counts ? m : (int64_t)1 << 21;
+    const uint4 *quartets = reinterpret_cast<const uint4 *>(d_quartets);
+    uint2 *rstat = reinterpret_cast<uint2 *>(d_rstat);
+
+    for (int64_t c0 = 0; c0 < m; c0 += chunk_cap) {
+        const int64_t mc = (m - c0 < chunk_cap) ? m - c0 : chunk_cap;
+        // scratch: cell_count | cell_off (+1) | flag | flag_scan (+1) | cell_fill | tile_list | tile_range | entries | counts | cub temp
+        size_t temp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)ncells + 1, stream);
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t cb = up(((size_t)ncells + 1) * 4);
+        const size_t o_count = 0, o_off = o_count + cb, o_flag = o_off + cb, o_fscan = o_flag + cb, o_fill = o_fscan + cb,
+                     o_list = o_fill + cb, o_range = o_list + cb, o_entries = o_range + 256, o_counts = o_entries + up((size_t)mc * 8),
+                     o_temp = o_counts + (d_counts ? 0 : up((size_t)mc * 1024)), total = o_temp + up(temp_bytes);
+        char *scratch = nullptr;
+        cudaError_t e = cudaMallocAsync(&scratch, total, stream);
+        if (e != cudaSuccess) return e;
+        uint32_t *cell_count = (uint32_t *)(scratch + o_count), *cell_off = (uint32_t *)(scratch + o_off);
+        uint32_t *flag = (uint32_t *)(scratch + o_flag), *fscan = (uint32_t *)(scratch + o_fscan);
+        uint32_t *cell_fill = (uint32_t *)(scratch + o_fill), *tile_list = (uint32_t *)(scratch + o_list);
+        uint32_t *tile_range = (uint32_t *)(scratch + o_range);
+        uint2 *entries = (uint2 *)(scratch + o_entries);
+        uint32_t *counts = d_counts ? d_counts + (size_t)c0 * 256 : (uint32_t *)(scratch + o_counts);
+
+        PG_CHECK(cudaMemsetAsync(scratch, 0, o_list, stream));            // counts, offsets, flags, scans, fills
+        const unsigned qb = (unsigned)((mc + 255) / 256), cbk = (ncells + 1 + 255) / 256;
+        pg_count_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_count, d_rscor + 3 * c0, rstat + c0, d_status);
+        PG_CHECK(cub::DeviceScan::ExclusiveSum(scratch + o_temp, temp_bytes, cell_count, cell_off, (int)ncells + 1, stream));
+        pg_flag_kernel<<<cbk, 256, 0, stream>>>(cell_count, ncells, flag);
+        PG_CHECK(cub::DeviceScan::ExclusiveSum(scratch + o_temp, temp_bytes, flag, fscan, (int)ncells + 1, stream));
+        pg_compact_kernel<<<cbk, 256, 0, stream>>>(cell_count, fscan, ncells, (uint32_t)num_sms, tile_list, tile_range);
+        pg_fill_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_off, cell_fill, entries);
+        g_launches += 7;
+        PG_CHECK(cudaGetLastError());
+
+        PairGemmArgs args;
+        args.planes = d_planes; args.row_u4 = plan.row_u4; args.ntips = n; args.npairs = np; args.ntc = ntc;
+        args.tile_list = tile_list; args.tile_range = tile_range; args.cell_off = cell_off; args.cell_count = cell_count;
+        args.entries = entries; args.counts = counts; args.desc_mode = (uint32_t)g_pairgemm_desc_mode.load();
+        // group g: GEMM on the caller's stream, its scores on the side stream behind an event -- beside the GEMM of g + 1
+        cudaEvent_t ev[kGroups + 1];
+        for (int g = 0; g <= kGroups; ++g) PG_CHECK(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+        for (int g = 0; g < kGroups; ++g) {
+            pair_gemm_kernel<<<num_sms, kGemmThreads, gemm_smem, stream>>>(args, g);
+            PG_CHECK(cudaEventRecord(ev[g], stream));
+            PG_CHECK(cudaStreamWaitEvent(side, ev[g], 0));
+            score_counts_kernel<<<num_sms, kScoreWarps * 32, score_smem, side>>>(counts, quartets + c0, entries, tile_list, tile_range,
+                                                                                 cell_off, cell_count, g, seed, d_rscor + 3 * c0,
+                                                                                 rstat + c0, d_minrank ? d_minrank + c0 : nullptr);
+            g_launches += 2;
+        }
+        PG_CHECK(cudaEventRecord(ev[kGroups], side));
+        PG_CHECK(cudaStreamWaitEvent(stream, ev[kGroups], 0));            // the caller's stream owns the results again
+        for (int g = 0; g <= kGroups; ++g) cudaEventDestroy(ev[g]);
+        PG_CHECK(cudaGetLastError());
+        cudaFreeAsync(scratch, stream);
+    }
+    g_last_kernel = "tq::pair_gemm_kernel (tcgen05.mma kind::i8) + tq::score_counts_kernel";
+    return cudaSuccess;
+}
+
+}  // namespace tq

@@ -1,0 +1,917 @@
+// Resolve kernels of the quartet-resolution hot path (sm_100a): fused count + score, only the result leaves the SM.
+//
+//   resolve_mma_kernel     the kernel large launches run.  8 count warps + 8 score warps per CTA, one CTA per SM.
+//                          Count warps: stage 1 selects one SNP per locus (running OR over the rank chunks of the four
+//                          tip rows), stage 2 forms the 256 site-pattern counts of every 1024-locus tile on the integer
+//                          tensor cores (IMMA.16832.U8.U8 on bit planes unpacked by one LOP3 per four loci).  The tip rows
+//                          reach shared memory either through a per-warp cp.async ring (kShared = false) or -- the eight
+//                          count warps of a CTA work on eight CONSECUTIVE quartets, which share most of their tips --
+//                          through ONE CTA-wide ring of TMA bulk copies that holds every distinct row of the batch once
+//                          (kShared = true: 11 rows instead of 32 per batch of an exhaustive list).  Score warps take four
+//                          finished quartets at a time through the FP64 QR + Jacobi of tq_svd.cuh.
+//   resolve_kernel         one warp per quartet, counts by AND + POPC with the packed counters in tensor memory
+//                          (tcgen05.alloc / ld / st), scores by the same tq_svd.cuh code: what small launches run (a
+//                          count -> score hand-off is pure latency when there are fewer quartets than warps).
+//   (full mode, dense quartet lists: tq_pairgemm.cu -- tcgen05.mma over tip pairs)
+//
+// launch_resolve picks by launch size; tq_set_option("kernel", ..) / TQ_KERNEL force one.  All give bit-identical results.
+// The measurements behind the constants (warp mix 8 + 8, ring depth 4, L1-bypassing cp.async, four mask scales, ...) are in
+// profiles/r01_v6_resolve_ncu.md and profiles/r01_v7_resolve_ncu.md; the build switches that produced them are in the
+// history of this file's predecessor (tq_kernels.cu, commit 425353e), not in the product.
+//
+// Reference semantics restated here (paths relative to the reference repo):
+//   tetrad/src/resolve_quartets.py:212-221  gather, missing mask, invariant mask
+//   tetrad/src/resolve_quartets.py:42-73    subsample_chunk_to_matrices (first usable SNP/locus)
+//   tetrad/src/resolve_quartets.py:76-104   full_chunk_to_matrices
+//   tetrad/src/resolve_quartets.py:226-264  nsnps, svd, matrix_rank, minrank, score, argmin
+//
+// Data layout: locus runs are sorted by length (longest first) and cut into tiles of 1024 loci; a tile
+// with K ranks stores, for every tip, K x 32 uint4 {A,C,G,T}: word `lane` of rank k holds, at bit b, the k-th column of
+// sorted locus 1024*tile+32*lane+b.  "First usable column of a locus" (the reference's last_loc state machine) is then
+// "lowest rank k whose bit survives the quartet's mask" -- a running OR per lane.
+#include "tq_kernels.cuh"
+#include "tq_device.cuh"
+#include "tq_svd.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace tq {
+
+std::atomic<int64_t> g_launches{0};
+std::atomic<const char *> g_last_kernel{"none"};
+// Kernel choice and test hooks (tq_set_option in the C ABI; the environment gives the initial values).
+//   g_kernel_choice: 0 = by launch size, 1 = fused (one warp per quartet, POPC), 3 = tensor-core count, per-warp cp.async rings,
+//                    4 = tensor-core count, CTA-shared TMA ring, 5 = tip-pair GEMM (full mode only)
+static int initial_kernel_choice()
+{
+    const char *e = getenv("TQ_KERNEL");
+    if (!e) return 0;
+    return !strcmp(e, "fused") ? 1 : !strcmp(e, "mma") ? 3 : !strcmp(e, "mma_shared") ? 4 : !strcmp(e, "pairgemm") ? 5 : 0;
+}
+static int64_t initial_mma_flush()
+{
+    const char *e = getenv("TQ_MMA_FLUSH");
+    return e ? atol(e) : 0;
+}
+std::atomic<int> g_kernel_choice{initial_kernel_choice()};
+std::atomic<int64_t> g_mma_flush{initial_mma_flush()};
+// 1: large launches stage the tip rows through the CTA-shared TMA ring; 0: through per-warp cp.async rings
+std::atomic<int> g_default_shared_ring{getenv("TQ_SHARED_RING") ? atoi(getenv("TQ_SHARED_RING")) : 1};
+
+static constexpr unsigned kFull = 0xFFFFFFFFu;
+static constexpr int kWarps = 4;                 // warps (= quartets in flight) per CTA of the fused kernel
+static constexpr int kStages = 4;                // cp.async ring depth (rank chunks in flight per warp)
+static constexpr uint32_t kFlushEvery = 63;      // POPC kernel: tile words between flushes of the packed 16-bit counters
+static constexpr uint32_t kTmemCols = 64;        // POPC kernel: tensor-memory columns per CTA (64 packed counters per thread)
+
+// cudaFuncSetAttribute is per device and must have RETURNED before any thread launches with > 48 KB of dynamic shared
+// memory: one mutex-guarded bit per device and kernel, set only after success.
+struct SmemAttr {
+    std::mutex mu;
+    uint64_t done = 0;
+    template <typename K>
+    cudaError_t ensure(K kern, size_t bytes)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const uint64_t bit = 1ull << (dev & 63);
+        std::lock_guard<std::mutex> lk(mu);
+        if (done & bit) return cudaSuccess;
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) done |= bit;
+        return e;
+    }
+};
+
+// ==========================================================================================
+// Small launches: one warp per quartet, AND + POPC counts with the counters in tensor memory
+// ==========================================================================================
+// Lane l owns locus word l of every tile (32 loci).  stage 1 as described above; stage 2: the 256 pattern counts of a
+// tile are popc(A_a & B_b & C_c & D_d) on the merged planes.  To halve the counters the two half-warps split the
+// patterns: lanes 0-15 count a in {0,1}, lanes 16-31 a in {2,3}, each for its own word and for the word of its partner
+// lane (l ^ 16), whose planes arrive by 14 warp shuffles.  Counter i packs two 16-bit counts: patterns (a, b, cd=2h) and
+// (a, b, cd=2h+1) with i = ((a & 1) * 4 + b) * 8 + h.  A lane adds at most 64 per call, the 16-lane butterfly of the flush
+// multiplies by 16, so flushing every 63 calls keeps every field below 65536.
+// Tensor memory as the counter file: a CTA (4 warps) allocates 64 columns; warp w owns TMEM lanes 32w..32w+31 of them,
+// i.e. every thread has 64 private 32-bit cells, which therefore do not occupy registers across tiles.
+struct __align__(16) WarpScratch {
+    union {
+        uint4 ring[kStages][4][32];             // stage-1 staging: [stage][tip][lane]      8 KB
+        SvdScratch4 svd;                        // the Jacobi reuses the ring once counting is over
+    };
+    uint32_t T[256];
+};
+
+// One (a,b) row = 16 patterns.  The ANDs and the POPCs are volatile asm so that ptxas keeps them in the order written:
+// a software pipeline in which every POPC has ~16 independent POPCs and the next row's ANDs between its issue and the add
+// that consumes it (left alone, ptxas puts the consumer 1-3 instructions behind the POPC and the warp sits on the XU
+// latency).
+__device__ __forceinline__ void row_and(uint32_t ab, const uint32_t (&C)[4], const uint32_t (&D)[4], uint32_t (&v)[16])
+{
+#pragma unroll
+    for (int cd = 0; cd < 16; ++cd)
+        asm volatile("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(v[cd]) : "r"(ab), "r"(C[cd >> 2]), "r"(D[cd & 3]));
+}
+__device__ __forceinline__ void row_popc(uint32_t (&v)[16])
+{
+#pragma unroll
+    for (int cd = 0; cd < 16; ++cd) asm volatile("popc.b32 %0, %0;" : "+r"(v[cd]));
+}
+__device__ __forceinline__ void row_add(const uint32_t (&v)[16], uint32_t *acc8)
+{
+#pragma unroll
+    for (int h = 0; h < 8; ++h) acc8[h] += v[2 * h] + (v[2 * h + 1] << 16);
+}
+
+// 256 pattern counts of one tile word pair (own word + partner lane's word), split by half-warp.
+__device__ __forceinline__ void count_tile(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                           const uint32_t (&MC)[4], const uint32_t (&MD)[4],
+                                           bool upper, uint32_t tacc)
+{
+    // planes the partner needs from me: the a-planes of ITS half, and all of B, C, D
+    const uint32_t sendA0 = upper ? MA[0] : MA[2], sendA1 = upper ? MA[1] : MA[3];
+    const uint32_t pA0 = __shfl_xor_sync(kFull, sendA0, 16), pA1 = __shfl_xor_sync(kFull, sendA1, 16);
+    uint32_t pB[4], pC[4], pD[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pB[i] = __shfl_xor_sync(kFull, MB[i], 16);
+        pC[i] = __shfl_xor_sync(kFull, MC[i], 16);
+        pD[i] = __shfl_xor_sync(kFull, MD[i], 16);
+    }
+    const uint32_t A0 = upper ? MA[2] : MA[0], A1 = upper ? MA[3] : MA[1];
+    tmem_wait_st();                                  // the previous tile's stores have landed
+    // counters 16g .. 16g+15 hold rows (ai, b) = (g / 2, 2 (g % 2) + {0, 1}).  A runtime loop: the counters are addressed
+    // in tensor memory, so nothing forces the 256 patterns to be unrolled, and the whole body (64 AND + 64 POPC + 64 add)
+    // stays resident in the instruction cache.
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        uint32_t acc[16];
+        tmem_ld16(tacc + 16 * g, acc);
+        const bool hi = (g & 1) != 0;
+        const uint32_t a_own = (g >> 1) ? A1 : A0, a_par = (g >> 1) ? pA1 : pA0;
+        const uint32_t o0 = a_own & (hi ? MB[2] : MB[0]), o1 = a_own & (hi ? MB[3] : MB[1]);
+        const uint32_t q0 = a_par & (hi ? pB[2] : pB[0]), q1 = a_par & (hi ? pB[3] : pB[1]);
+        uint32_t va[16], vb[16];
+        row_and(o0, MC, MD, va);
+        row_popc(va);
+        row_and(o1, MC, MD, vb);
+        tmem_wait_ld();
+        row_add(va, acc);
+        row_popc(vb);
+        row_and(q0, pC, pD, va);
+        row_add(vb, acc + 8);
+        row_popc(va);
+        row_and(q1, pC, pD, vb);
+        row_add(va, acc);
+        row_popc(vb);
+        row_add(vb, acc + 8);
+        tmem_st16(tacc + 16 * g, acc);
+    }
+}
+
+__device__ __forceinline__ void zero_acc(uint32_t tacc)
+{
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+    tmem_wait_st();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) tmem_st16(tacc + 16 * g, z);
+}
+
+// Read the 64 packed counters back from tensor memory, butterfly-add them over the 16 lanes of each half-warp, add into
+// T, and clear them.  Runtime loop over the four groups (code size).
+__device__ __noinline__ void flush_tmem(uint32_t tacc, uint32_t *T, int lane)
+{
+    const int abase = (lane >> 4) * 2;           // first a-value of this half-warp
+    tmem_wait_st();
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        uint32_t part[16];
+        tmem_ld16(tacc + 16 * g, part);
+        tmem_wait_ld();
+        uint32_t *row = T + ((abase + (g >> 1)) * 4 + 2 * (g & 1)) * 16;      // pattern (a, b = 2(g%2), cd = 0)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            uint32_t v = part[k];
+            v += __shfl_xor_sync(kFull, v, 8);
+            v += __shfl_xor_sync(kFull, v, 4);
+            v += __shfl_xor_sync(kFull, v, 2);
+            v += __shfl_xor_sync(kFull, v, 1);
+            if ((lane & 15) == k) {                                            // k = 8 (b & 1) + h
+                uint2 *t = reinterpret_cast<uint2 *>(row + (k >> 3) * 16 + 2 * (k & 7));
+                uint2 cur = *t;
+                cur.x += v & 0xFFFFu;
+                cur.y += v >> 16;
+                *t = cur;
+            }
+            part[k] = 0u;
+        }
+        tmem_st16(tacc + 16 * g, part);
+    }
+}
+
+// Issue the four 16-byte cp.async of rank chunk `nu` (one per tip) into ring stage nu % kStages.
+// All global addressing is a 32-bit uint4 index off `planes` (the host checks ntips*row_u4 < 2^32).
+__device__ __forceinline__ void issue_chunk(uint32_t ring_s, const uint4 *__restrict__ planes, uint32_t lane_nu,
+                                            uint32_t stage, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3)
+{
+    const uint32_t s = ring_s + stage * (4 * 32 * 16);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(planes + (t0 + lane_nu)) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 512), "l"(planes + (t1 + lane_nu)) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1024), "l"(planes + (t2 + lane_nu)) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s + 1536), "l"(planes + (t3 + lane_nu)) : "memory");
+}
+
+template <bool kSubsample>
+__device__ __forceinline__ void count_quartet(const PlanDev &plan, const uint4 *__restrict__ planes,
+                                              uint4 tips, const uint4 *ring, uint32_t *T, int lane, uint32_t tacc)
+{
+    const bool upper = lane >= 16;
+    uint32_t pending = 0;
+    const uint32_t nchunks = plan.row_u4 / kTileWords;
+    const uint32_t t0 = tips.x * plan.row_u4, t1 = tips.y * plan.row_u4;    // row starts, uint4 units
+    const uint32_t t2 = tips.z * plan.row_u4, t3 = tips.w * plan.row_u4;
+    const uint32_t ring_s = smem_u32(ring + lane);
+
+    // prologue: chunks 0 .. kStages-2 in flight
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if ((uint32_t)s < nchunks) issue_chunk(ring_s, planes, s * kTileWords + lane, s, t0, t1, t2, t3);
+        cp_async_commit();
+    }
+
+    uint32_t u = 0;                                   // rank-chunk index along the rows
+    for (int tile = 0; tile < plan.ntiles; ++tile) {
+        const uint32_t K = __ldg(plan.tile_k + tile);
+        uint32_t taken = 0u;
+        uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
+        uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
+        for (uint32_t k = 0; k < K; ++k, ++u) {
+            {   // keep kStages-1 chunks in flight
+                const uint32_t nu = u + kStages - 1;
+                if (nu < nchunks) issue_chunk(ring_s, planes, nu * kTileWords + lane, nu % kStages, t0, t1, t2, t3);
+                cp_async_commit();
+            }
+            cp_async_wait<kStages - 1>();
+            const int s = u % kStages;
+            const uint4 *st = ring + s * (4 * 32) + lane;
+            const uint4 a = st[0], b = st[32], c = st[64], d = st[96];
+            if (kSubsample) {
+                const uint32_t valid = (a.x | a.y | a.z | a.w) & (b.x | b.y | b.z | b.w) &
+                                       (c.x | c.y | c.z | c.w) & (d.x | d.y | d.z | d.w);
+                const uint32_t same = (a.x & b.x & c.x & d.x) | (a.y & b.y & c.y & d.y) |
+                                      (a.z & b.z & c.z & d.z) | (a.w & b.w & c.w & d.w);
+                const uint32_t sel = valid & ~same & ~taken;
+                taken |= sel;
+                MA[0] |= a.x & sel; MA[1] |= a.y & sel; MA[2] |= a.z & sel; MA[3] |= a.w & sel;
+                MB[0] |= b.x & sel; MB[1] |= b.y & sel; MB[2] |= b.z & sel; MB[3] |= b.w & sel;
+                MC[0] |= c.x & sel; MC[1] |= c.y & sel; MC[2] |= c.z & sel; MC[3] |= c.w & sel;
+                MD[0] |= d.x & sel; MD[1] |= d.y & sel; MD[2] |= d.z & sel; MD[3] |= d.w & sel;
+            } else {
+                // full mode (resolve_quartets.py:92-95): every complete column counts; the four
+                // invariant patterns aaaa are zeroed by the caller
+                const uint32_t A[4] = {a.x, a.y, a.z, a.w}, B[4] = {b.x, b.y, b.z, b.w};
+                const uint32_t C[4] = {c.x, c.y, c.z, c.w}, D[4] = {d.x, d.y, d.z, d.w};
+                count_tile(A, B, C, D, upper, tacc);
+                if (++pending == kFlushEvery) { flush_tmem(tacc, T, lane); pending = 0; }
+            }
+        }
+        if (kSubsample) {
+            count_tile(MA, MB, MC, MD, upper, tacc);
+            if (++pending == kFlushEvery) { flush_tmem(tacc, T, lane); pending = 0; }
+        }
+    }
+    cp_async_wait<0>();
+    flush_tmem(tacc, T, lane);
+}
+
+// What every kernel does with a finished count tensor T[256] of a quartet whose tips are in range: zero the invariant
+// patterns in full mode (:218), nsnps (:226), optional export; returns nsnps (warp-uniform).
+template <bool kSubsample>
+__device__ __forceinline__ uint32_t finish_counts(uint32_t *T, int lane, uint32_t *__restrict__ counts, long long q)
+{
+    if (!kSubsample && lane < 4) T[85u * lane] = 0u;   // invariant patterns aaaa, :218
+    __syncwarp();
+    uint32_t nsnps = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t v = T[lane + 32 * i];
+        nsnps += v;
+        if (counts) counts[q * 256 + lane + 32 * i] = v;
+    }
+    return __reduce_add_sync(kFull, nsnps);                             // :226
+}
+
+template <bool kSubsample>
+__global__ void __launch_bounds__(kWarps * 32, 4)
+resolve_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
+               const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
+               double *__restrict__ rscor, uint2 *__restrict__ rstat,
+               uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
+               uint32_t *__restrict__ status)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WarpScratch &ws = scratch[warp];
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    __shared__ uint32_t tmem_base_slot;
+    if (warp == 0) tmem_alloc(&tmem_base_slot, kTmemCols);   // one warp allocates (and later frees) the CTA's columns
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quadrant
+    zero_acc(tacc);
+
+    for (int64_t q = (int64_t)blockIdx.x * kWarps + warp; q < m; q += nwarps) {
+        const uint4 t = __ldg(quartets + q);
+        if (t.x >= ntips || t.y >= ntips || t.z >= ntips || t.w >= ntips) {
+            if (lane == 0) {
+                rstat[q] = make_uint2(0xFFFFFFFFu, 0u);
+                rscor[3 * q] = rscor[3 * q + 1] = rscor[3 * q + 2] = 0.0;
+                if (status) atomicOr(status, 1u);
+            }
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ws.T[lane + 32 * i] = 0u;
+        __syncwarp();
+        count_quartet<kSubsample>(plan, planes, t, &ws.ring[0][0][0], ws.T, lane, tacc);
+        __syncwarp();
+        const uint32_t nsnps = finish_counts<kSubsample>(ws.T, lane, counts, q);
+        double score[3] = {0.001, 0.001, 0.001};                        // :232
+        uint32_t best = 0, minrank = 0;
+        if (nsnps == 0) best = tiebreak_split(seed, t);                 // stands in for :231
+        else svd_scores4(ws.T, 0u, 1u, ws.svd, lane, score, best, minrank);   // one quartet: pass 0, matrices 0..2
+        if (lane == 0) {
+            rscor[3 * q] = score[0]; rscor[3 * q + 1] = score[1]; rscor[3 * q + 2] = score[2];
+            rstat[q] = make_uint2(best, nsnps);                         // :251, :264
+            if (minrank_out) minrank_out[q] = minrank;
+        }
+        __syncwarp();
+    }
+    tmem_wait_st();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ==========================================================================================
+// Large launches: stage 2 on the integer tensor cores
+// ==========================================================================================
+//   T[ab][cd] = sum over the tile's 1024 loci of  X_ab[l] * Y_cd[l],   X_ab = A_a & B_b,  Y_cd = C_c & D_d
+//
+// is a 16 x 16 x 1024 product of 0/1 matrices whose rows ARE the merged bit planes.  sm_100a has no native 1-bit MMA
+// (ptxas expands mma.b1 into IMMA + ~100 unpack instructions), but the legacy u8 instruction mma.sync.m16n8k32 (SASS
+// IMMA.16832.U8.U8) is native, and a bit plane becomes an u8 operand with ONE LOP3 per four loci: word & (0x01010101 << v)
+// holds the bytes {0, 2^v}.  Both operands use the same mask, so all products of one instruction are {0, 4^v}; v = 0..3 on
+// the word and on the word >> 4 cover the eight bits of every byte, and each v has its own s32 accumulator fragment:
+// count = sum_v acc_v >> 2v.  The K order of an MMA is free as long as A and B agree, so lane (g = lane / 4, j = lane % 4)
+// simply feeds bytes j of ITS OWN word pair -- the data is never transposed: the lane reads planes A_p, A_p+2, B_r (rows g
+// and g + 8 of the A operand, p = g / 4, r = g % 4) and C_p, C_p+2, D_r (column g of the two B operands) of words 8 j ..
+// 8 j + 7 from a per-warp shared-memory copy of the tile's 16 merged planes (row stride 34 words: conflict-free 8-byte
+// reads).  Per tile and warp: 16 STS + 24 LDS.64 + ~320 LOP3/SHF + 64 IMMA; nothing runs on the XU pipe, the MMA sums over
+// the whole tile (no cross-lane butterfly), and the counters are 32 registers.  (Why not tcgen05 here: the operands are
+// per quartet -- the selected column of a locus depends on all four tips -- and 16 x 16 x 1024 is far below a tcgen05 tile;
+// batching eight quartets into one 128 x 128 tile computes 64 blocks to use 8.  Full mode, where the operands belong to
+// tip PAIRS, does use it: tq_pairgemm.cu.)
+static constexpr int kMStages = 4;                  // ring depth (per-warp cp.async ring and CTA-shared TMA ring)
+static constexpr int kScales = 4;
+static constexpr int kPStride = 34;                 // words per plane row of the per-warp tile copy
+static constexpr uint32_t kMmaFlushEvery = 16384;   // tile products between accumulator flushes: 16384 * 1024 * 4^3 < 2^31
+                                                    // (tq_set_option("mma_flush_every") lowers it so that tests reach the flush)
+static constexpr int kNC = 8, kNS = 8;              // count / score warps per CTA (measured mixes: profiles/r01_v7_resolve_ncu.md)
+
+__device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// acc[v][h][i]: scale 4^v, column half h (cd = 8h ..), fragment register i
+struct MmaLanePtrs {              // per-lane views of the warp's tile copy P, set up once per quartet
+    uint32_t *st;                 // P + lane: where this lane stores its word of every plane
+    const uint32_t *pa;           // A_p words 8j..: A_p+2 two rows on, C_p eight rows on, C_p+2 ten rows on
+    const uint32_t *pb;           // B_r words 8j..: D_r eight rows on
+};
+__device__ __forceinline__ MmaLanePtrs mma_lane_ptrs(uint32_t *P, int lane)
+{
+    const int g = lane >> 2, j = lane & 3;
+    MmaLanePtrs lp;
+    lp.st = P + lane;
+    lp.pa = P + (g >> 2) * kPStride + 8 * j;
+    lp.pb = P + (4 + (g & 3)) * kPStride + 8 * j;
+    return lp;
+}
+
+__device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                               const uint32_t (&MC)[4], const uint32_t (&MD)[4],
+                                               const MmaLanePtrs &lp, int (&acc)[kScales][2][4])
+{
+    __syncwarp();                                    // the previous tile's reads are over
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        lp.st[(0 + k) * kPStride] = MA[k];
+        lp.st[(4 + k) * kPStride] = MB[k];
+        lp.st[(8 + k) * kPStride] = MC[k];
+        lp.st[(12 + k) * kPStride] = MD[k];
+    }
+    __syncwarp();
+    const uint32_t *pa = lp.pa, *pb = lp.pb;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint2 a0 = *reinterpret_cast<const uint2 *>(pa + 2 * i);
+        const uint2 a1 = *reinterpret_cast<const uint2 *>(pa + 2 * kPStride + 2 * i);
+        const uint2 b = *reinterpret_cast<const uint2 *>(pb + 2 * i);
+        const uint2 c0 = *reinterpret_cast<const uint2 *>(pa + 8 * kPStride + 2 * i);
+        const uint2 c1 = *reinterpret_cast<const uint2 *>(pa + 10 * kPStride + 2 * i);
+        const uint2 d = *reinterpret_cast<const uint2 *>(pb + 8 * kPStride + 2 * i);
+        uint32_t x[2][4], y[2][4];    // x: rows g / g+8 of word W, then of word W';  y: column g of half 0 (W, W'), of half 1 (W, W')
+        x[0][0] = a0.x & b.x; x[0][1] = a1.x & b.x; x[0][2] = a0.y & b.y; x[0][3] = a1.y & b.y;
+        y[0][0] = c0.x & d.x; y[0][1] = c0.y & d.y; y[0][2] = c1.x & d.x; y[0][3] = c1.y & d.y;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { x[1][q] = x[0][q] >> 4; y[1][q] = y[0][q] >> 4; }
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const uint32_t msk = 0x01010101u << v;
+                const uint32_t f0 = x[s][0] & msk, f1 = x[s][1] & msk, f2 = x[s][2] & msk, f3 = x[s][3] & msk;
+                imma_u8(acc[v][0], f0, f1, f2, f3, y[s][0] & msk, y[s][1] & msk);
+                imma_u8(acc[v][1], f0, f1, f2, f3, y[s][2] & msk, y[s][3] & msk);
+            }
+    }
+}
+
+// Add the accumulated counts into T and clear the accumulators.  Lane (g, j) holds rows g and g + 8,
+// columns 2j and 2j + 1 of each column half: no cross-lane step.
+__device__ __forceinline__ void flush_mma(int (&acc)[kScales][2][4], uint32_t *T, int lane)
+{
+    const int g = lane >> 2, j = lane & 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            uint32_t c0 = 0u, c1 = 0u;
+#pragma unroll
+            for (int v = 0; v < kScales; ++v) {
+                c0 += (uint32_t)acc[v][h][2 * rr] >> (2 * v);
+                c1 += (uint32_t)acc[v][h][2 * rr + 1] >> (2 * v);
+                acc[v][h][2 * rr] = 0; acc[v][h][2 * rr + 1] = 0;
+            }
+            uint2 *t = reinterpret_cast<uint2 *>(T + (g + 8 * rr) * 16 + 8 * h + 2 * j);
+            uint2 cur = *t;
+            cur.x += c0; cur.y += c1;
+            *t = cur;
+        }
+}
+
+// One rank chunk of stage 1 (subsample mode): sel = complete & segregating & ~taken; a selected column is complete, so
+// the T plane of every tip is what the other three leave of `taken`: three merged planes per tip are updated per chunk,
+// the fourth is derived once per tile (finish_tile_planes).
+__device__ __forceinline__ void select_chunk(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, uint32_t &taken,
+                                             uint32_t (&MA)[4], uint32_t (&MB)[4], uint32_t (&MC)[4], uint32_t (&MD)[4])
+{
+    const uint32_t valid = (a.x | a.y | a.z | a.w) & (b.x | b.y | b.z | b.w) &
+                           (c.x | c.y | c.z | c.w) & (d.x | d.y | d.z | d.w);
+    const uint32_t same = (a.x & b.x & c.x & d.x) | (a.y & b.y & c.y & d.y) |
+                          (a.z & b.z & c.z & d.z) | (a.w & b.w & c.w & d.w);
+    const uint32_t sel = valid & ~same & ~taken;
+    taken |= sel;
+    MA[0] |= a.x & sel; MA[1] |= a.y & sel; MA[2] |= a.z & sel;
+    MB[0] |= b.x & sel; MB[1] |= b.y & sel; MB[2] |= b.z & sel;
+    MC[0] |= c.x & sel; MC[1] |= c.y & sel; MC[2] |= c.z & sel;
+    MD[0] |= d.x & sel; MD[1] |= d.y & sel; MD[2] |= d.z & sel;
+}
+__device__ __forceinline__ void finish_tile_planes(uint32_t taken, uint32_t (&MA)[4], uint32_t (&MB)[4], uint32_t (&MC)[4],
+                                                   uint32_t (&MD)[4])
+{
+    MA[3] = taken & ~(MA[0] | MA[1] | MA[2]); MB[3] = taken & ~(MB[0] | MB[1] | MB[2]);
+    MC[3] = taken & ~(MC[0] | MC[1] | MC[2]); MD[3] = taken & ~(MD[0] | MD[1] | MD[2]);
+}
+
+// Per-warp ring: stage 1 by cp.async (L1-bypassing .cg: consecutive quartets' shared rows hitting in L1 was measured 3 %
+// slower), stage 2 by count_tile_mma.  The tile's rank count is fetched one tile ahead, the ring reads are issued before
+// the next chunk's address arithmetic and cp.async so that their latency is covered, and the global addresses are four
+// 64-bit row pointers plus one running 32-bit offset.
+template <bool kSubsample>
+__device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uint4 *__restrict__ planes,
+                                                  uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane,
+                                                  uint32_t flush_every)
+{
+    static_assert((kMStages & (kMStages - 1)) == 0, "ring depth must be a power of two");
+    int acc[kScales][2][4];
+#pragma unroll
+    for (int v = 0; v < kScales; ++v)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[v][h][i] = 0;
+    const MmaLanePtrs lp = mma_lane_ptrs(P, lane);
+    uint32_t pending = 0;
+    const uint32_t nchunks = plan.row_u4 / kTileWords;
+    const uint4 *g0 = planes + (size_t)tips.x * plan.row_u4 + lane, *g1 = planes + (size_t)tips.y * plan.row_u4 + lane;
+    const uint4 *g2 = planes + (size_t)tips.z * plan.row_u4 + lane, *g3 = planes + (size_t)tips.w * plan.row_u4 + lane;
+    const uint32_t ring_s = smem_u32(ring + lane);
+    auto issue = [&](uint32_t chunk) {
+        const uint32_t s = ring_s + (chunk & (kMStages - 1)) * (4 * 32 * 16), off = chunk * kTileWords;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g0 + off) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s + 512), "l"(g1 + off) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s + 1024), "l"(g2 + off) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s + 1536), "l"(g3 + off) : "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < kMStages - 1; ++s) {
+        if ((uint32_t)s < nchunks) issue(s);
+        cp_async_commit();
+    }
+    uint32_t u = 0;                                   // rank-chunk index along the rows
+    const int ntiles = plan.ntiles;
+    uint32_t Knext = ntiles > 0 ? __ldg(plan.tile_k) : 0u;
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const uint32_t K = Knext;
+        if (tile + 1 < ntiles) Knext = __ldg(plan.tile_k + tile + 1);
+        uint32_t taken = 0u;
+        uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
+        uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
+        for (uint32_t k = 0; k < K; ++k, ++u) {
+            cp_async_wait<kMStages - 2>();            // chunk u has landed (chunks u+1 .. u+kMStages-2 may be in flight)
+            const uint4 *st = ring + (u & (kMStages - 1)) * (4 * 32) + lane;
+            const uint4 a = st[0], b = st[32], c = st[64], d = st[96];
+            {   // refill the stage read in the previous iteration; keeps kMStages-1 chunks in flight
+                const uint32_t nu = u + kMStages - 1;
+                if (nu < nchunks) issue(nu);
+                cp_async_commit();
+            }
+            if (kSubsample) {
+                select_chunk(a, b, c, d, taken, MA, MB, MC, MD);
+            } else {
+                // full mode (resolve_quartets.py:92-95): every complete column counts; the four
+                // invariant patterns aaaa are zeroed by the caller
+                const uint32_t A[4] = {a.x, a.y, a.z, a.w}, B[4] = {b.x, b.y, b.z, b.w};
+                const uint32_t C[4] = {c.x, c.y, c.z, c.w}, D[4] = {d.x, d.y, d.z, d.w};
+                count_tile_mma(A, B, C, D, lp, acc);
+                if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
+            }
+        }
+        if (kSubsample) {
+            finish_tile_planes(taken, MA, MB, MC, MD);
+            count_tile_mma(MA, MB, MC, MD, lp, acc);
+            if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
+        }
+    }
+    cp_async_wait<0>();
+    flush_mma(acc, T, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-shared ring (kShared).  The NC count warps of a CTA always work on NC CONSECUTIVE quartets ("a batch").  In a
+// lexicographic list consecutive quartets differ in their last tip only, so a batch of 8 touches 11 distinct tip rows,
+// not 32 (a sorted random sample: ~20).  The rows of the batch are deduplicated (32 tip ids, one per lane:
+// __match_any_sync) and every DISTINCT row's rank chunk is brought in ONCE per stage by a TMA bulk copy
+// (cp.async.bulk, 512 B per row and stage) that completes on the stage's mbarrier; a stage is a slot of up to 32 rows
+// (16 KB), the ring has kMStages slots.  No warp is a producer: the count warp that finishes a stage LAST (one
+// shared-memory atomic per warp and stage) re-arms the slot and issues the copies of the stage kMStages ahead -- which
+// may already belong to the next batch, so the stream never drains between batches.  The count warps issue no LDGSTS,
+// compute no global addresses, and L2 -> SM traffic drops by the sharing factor.
+// ------------------------------------------------------------------------------------------
+static constexpr int kSlotRows = 4 * kNC;            // rows a stage can hold (no sharing at all: 4 per quartet)
+
+struct __align__(16) WsSlotMeta { long long q; uint4 tips; };   // hand-off slot: quartet index (or -1 - q: bad tips) and tips
+
+struct BatchRows {                // per-lane view of a batch's distinct rows (identical in every count warp)
+    uint32_t nd;                  // distinct rows of the batch
+    const uint4 *row;             // lane i < nd: start of distinct row i in global memory
+    uint32_t off[4];              // uint4 offset, inside a stage, of THIS lane's word of THIS warp's four tips
+};
+
+// tips of quartet (lane / 4) of the batch, tip (lane % 4); out-of-range / missing quartets read row 0 (never published)
+__device__ __forceinline__ BatchRows dedupe_batch(const uint4 *__restrict__ planes, uint32_t row_u4, uint32_t my_tip, int lane, int c)
+{
+    const uint32_t same = __match_any_sync(kFull, my_tip);
+    const bool leader = (uint32_t)(__ffs(same) - 1) == (uint32_t)lane;
+    const uint32_t leaders = __ballot_sync(kFull, leader);
+    const uint32_t my_slot = __popc(leaders & ((1u << (__ffs(same) - 1)) - 1u));       // rank of my leader among the leaders
+    BatchRows br;
+    br.nd = __popc(leaders);
+    const int src = (lane < (int)br.nd) ? (int)__fns(leaders, 0, lane + 1) : 0;       // lane of the leader with slot == lane
+    const uint32_t tip = __shfl_sync(kFull, my_tip, src);
+    br.row = planes + (size_t)tip * row_u4;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) br.off[t] = __shfl_sync(kFull, my_slot, 4 * c + t) * 32u + (uint32_t)lane;
+    return br;
+}
+
+template <int NC, int NS>
+struct __align__(16) MmaShared {
+    static constexpr int kSlots = NC + 4 * NS;      // every count warp fills one slot, every score warp holds up to four
+    uint4 ring[NC][kMStages][4][32];                // per-warp rings; the CTA-shared ring uses the same 64 KB as
+                                                    // [kMStages][kSlotRows][32]
+    uint32_t P[NC][16 * kPStride];
+    uint32_t T[kSlots][256];
+    WsSlotMeta meta[kSlots];
+    SvdScratch4 svd[NS];
+    unsigned long long full[kSlots], empty[kSlots];
+    unsigned long long ring_full[kMStages];         // CTA-shared ring: bulk-copy completion barrier of every stage
+    uint32_t ring_done[kMStages];                   // count warps that have finished reading the stage
+    uint32_t produce, consume;
+};
+
+template <bool kSubsample, bool kShared, int NC, int NS>
+__global__ void __launch_bounds__((NC + NS) * 32, 1)
+resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
+                   const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
+                   double *__restrict__ rscor, uint2 *__restrict__ rstat,
+                   uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
+                   uint32_t *__restrict__ status, uint32_t flush_every)
+{
+    using Shared = MmaShared<NC, NS>;
+    constexpr int kSlots = Shared::kSlots;
+    static_assert(kSlots <= 256, "slot indices travel in one byte each");
+    static_assert(!kShared || NC == 8, "the batch deduplication maps one tip to one lane: 8 quartets x 4 tips");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared &sh = *reinterpret_cast<Shared *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSlots; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+        for (int s = 0; s < kMStages; ++s) { mbar_init(&sh.ring_full[s], 1); sh.ring_done[s] = 0u; }
+        sh.produce = 0u; sh.consume = 0u;
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    // Work split: batch b = blockIdx.x + it * gridDim.x holds quartets b * NC .. b * NC + NC - 1, one per count warp.
+    const int64_t nbatches = (m + NC - 1) / NC;
+    const int64_t my_batches = (int64_t)blockIdx.x < nbatches ? (nbatches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // quartets this CTA resolves (the last batch may be short)
+    int64_t total = my_batches * NC;
+    {
+        const int64_t last_b = (int64_t)blockIdx.x + (my_batches - 1) * gridDim.x;
+        if (my_batches > 0 && last_b == nbatches - 1) total -= nbatches * NC - m;
+    }
+
+    if (warp < NC) {
+        // ------------------------------ count warps ------------------------------
+        const int c = warp;
+        const uint32_t nchunks = plan.row_u4 / kTileWords;
+        // CTA-shared ring state, the same sequence in every count warp: slot rs and phase parity ph of the next stage.
+        // The ring has RS = min(kMStages, nchunks) slots, so the stage RS ahead of a chunk of batch `it` belongs to
+        // batch it or it + 1, never further.
+        const uint32_t RS = nchunks < (uint32_t)kMStages ? nchunks : (uint32_t)kMStages;
+        uint32_t rs = 0u, ph = 0u;
+        uint32_t cur_nd = 0u, nxt_nd = 0u;
+        const uint4 *cur_row = planes, *nxt_row = planes;                     // lane i: distinct row i of the batch / the next one
+        uint32_t off0 = 0u, off1 = 0u, off2 = 0u, off3 = 0u;
+        auto load_rows = [&](int64_t it) -> BatchRows {                      // rows of this CTA's it-th batch
+            uint32_t tip = 0u;
+            if (it < my_batches) {
+                const int64_t qq = ((int64_t)blockIdx.x + it * gridDim.x) * NC + (lane >> 2);
+                if (qq < m) {
+                    const uint32_t *qt = reinterpret_cast<const uint32_t *>(quartets + qq);
+                    tip = __ldg(qt + (lane & 3));
+                    if (tip >= ntips) tip = 0u;
+                }
+            }
+            return dedupe_batch(planes, plan.row_u4, tip, lane, c);
+        };
+        // bulk copies of one stage: rank chunk `chunk` of the `nd` distinct rows `row` into ring slot `slot`
+        auto issue_stage = [&](uint32_t slot, uint32_t chunk, uint32_t nd, const uint4 *row) {
+            unsigned long long *bar = &sh.ring_full[slot];
+            if (lane == 0) mbar_arrive_expect_tx(bar, nd * 512u);
+            __syncwarp();
+            if (lane < (int)nd)
+                bulk_copy_g2s(smem_u32(&sh.ring[0][0][0][0]) + slot * (kSlotRows * 512u) + (uint32_t)lane * 512u,
+                              row + (size_t)chunk * kTileWords, 512u, bar);
+        };
+        if (kShared && my_batches > 0 && nchunks > 0) {
+            const BatchRows b0 = load_rows(0), b1 = load_rows(1);
+            cur_nd = b0.nd; cur_row = b0.row; off0 = b0.off[0]; off1 = b0.off[1]; off2 = b0.off[2]; off3 = b0.off[3];
+            nxt_nd = b1.nd; nxt_row = b1.row;
+            if (c == 0)                                    // prologue: the first RS stages of the stream (RS <= nchunks: batch 0)
+                for (uint32_t i = 0; i < RS; ++i) issue_stage(i, i, cur_nd, cur_row);
+        }
+        for (int64_t it = 0; it < my_batches; ++it) {
+            const int64_t q = ((int64_t)blockIdx.x + it * gridDim.x) * NC + c;
+            const bool present = q < m;
+            uint32_t ticket = 0, slot = 0;
+            uint32_t *T = nullptr;
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            bool bad = false;
+            if (present) {
+                if (lane == 0) ticket = atomicAdd(&sh.produce, 1u);
+                ticket = __shfl_sync(kFull, ticket, 0);
+                slot = ticket % kSlots;
+                mbar_wait(&sh.empty[slot], ((ticket / kSlots) & 1u) ^ 1u);   // slot free (passes at once on its first use)
+                T = sh.T[slot];
+                t = __ldg(quartets + q);
+                bad = t.x >= ntips || t.y >= ntips || t.z >= ntips || t.w >= ntips;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
+                __syncwarp();
+            }
+            if constexpr (!kShared) {
+                if (present && !bad)
+                    count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every);
+            } else if (nchunks > 0) {     // (kShared)
+                // ---- stage 1 from the CTA-shared ring; every count warp walks the same stages, present or not ----
+                const bool work = present && !bad;
+                int acc[kScales][2][4];
+#pragma unroll
+                for (int v = 0; v < kScales; ++v)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[v][h][i] = 0;
+                const MmaLanePtrs lp = mma_lane_ptrs(sh.P[c], lane);
+                uint32_t pending = 0;
+                const uint4 *ringbase = &sh.ring[0][0][0][0];
+                const bool more = it + 1 < my_batches;                 // the stream goes on into another batch
+                const int ntiles = plan.ntiles;
+                uint32_t Knext = ntiles > 0 ? __ldg(plan.tile_k) : 0u;
+                uint32_t u = 0;                                        // rank-chunk index along the rows
+                for (int tile = 0; tile < ntiles; ++tile) {
+                    const uint32_t K = Knext;
+                    if (tile + 1 < ntiles) Knext = __ldg(plan.tile_k + tile + 1);
+                    uint32_t taken = 0u;
+                    uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
+                    uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
+                    for (uint32_t k = 0; k < K; ++k, ++u) {
+                        mbar_wait_short(&sh.ring_full[rs], ph);        // the stage has landed
+                        const uint4 *st = ringbase + rs * (kSlotRows * 32);
+                        const uint4 a = st[off0], b = st[off1], cc = st[off2], d = st[off3];
+                        __syncwarp();                                  // every lane's reads of the stage have been issued
+                        uint32_t last = 0u;
+                        if (lane == 0) {
+                            uint32_t old;
+                            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;\n"
+                                         : "=r"(old) : "r"(smem_u32(&sh.ring_done[rs])) : "memory");
+                            last = old == (uint32_t)(NC - 1);
+                            if (last) sh.ring_done[rs] = 0u;           // re-armed before the copies below can complete
+                        }
+                        last = __shfl_sync(kFull, last, 0);
+                        if (last) {                                    // this warp read the stage last: refill its slot
+                            const uint32_t nu = u + RS;                // with the stage RS ahead in the stream
+                            if (nu < nchunks) issue_stage(rs, nu, cur_nd, cur_row);
+                            else if (more) issue_stage(rs, nu - nchunks, nxt_nd, nxt_row);
+                        }
+                        if (++rs == RS) { rs = 0u; ph ^= 1u; }
+                        if (work) {
+                            if (kSubsample) {
+                                select_chunk(a, b, cc, d, taken, MA, MB, MC, MD);
+                            } else {
+                                const uint32_t A[4] = {a.x, a.y, a.z, a.w}, B[4] = {b.x, b.y, b.z, b.w};
+                                const uint32_t C[4] = {cc.x, cc.y, cc.z, cc.w}, D[4] = {d.x, d.y, d.z, d.w};
+                                count_tile_mma(A, B, C, D, lp, acc);
+                                if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
+                            }
+                        }
+                    }
+                    if (kSubsample && work) {
+                        finish_tile_planes(taken, MA, MB, MC, MD);
+                        count_tile_mma(MA, MB, MC, MD, lp, acc);
+                        if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
+                    }
+                }
+                if (work) flush_mma(acc, T, lane);
+                {   // the next batch becomes the current one; look one further ahead
+                    const BatchRows b1 = load_rows(it + 1), b2 = load_rows(it + 2);
+                    cur_nd = b1.nd; cur_row = b1.row; off0 = b1.off[0]; off1 = b1.off[1]; off2 = b1.off[2]; off3 = b1.off[3];
+                    nxt_nd = b2.nd; nxt_row = b2.row;
+                }
+            }
+            if (present) {
+                if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.full[slot]);
+            }
+        }
+    } else {
+        // ------------------------------ score warps ------------------------------
+        // A score warp takes up to four finished quartets at a time (svd_scores4: 12 matrices in three passes of four).
+        SvdScratch4 &sv = sh.svd[warp - NC];
+        while (true) {
+            uint32_t ticket0 = 0;
+            if (lane == 0) ticket0 = atomicAdd(&sh.consume, 4u);
+            ticket0 = __shfl_sync(kFull, ticket0, 0);
+            if ((int64_t)ticket0 >= total) break;
+            const int nq = (int)((total - (int64_t)ticket0) < 4 ? (total - (int64_t)ticket0) : 4);
+            uint32_t slots = 0u, actmask = 0u, my_nsnps = 0u, my_best = 0u;
+            long long my_q = -1;                                           // lane j < 4: quartet j of this batch
+#pragma unroll 1
+            for (int j = 0; j < nq; ++j) {
+                const uint32_t ticket = ticket0 + (uint32_t)j;
+                const uint32_t slot = ticket % kSlots;
+                mbar_wait(&sh.full[slot], (ticket / kSlots) & 1u);
+                slots |= slot << (8 * j);
+                uint32_t *T = sh.T[slot];
+                const long long mq = sh.meta[slot].q;
+                const uint4 t = sh.meta[slot].tips;
+                if (mq < 0) {                                              // tip index out of range
+                    const long long q = -1 - mq;
+                    if (lane == 0) {
+                        rstat[q] = make_uint2(0xFFFFFFFFu, 0u);
+                        rscor[3 * q] = rscor[3 * q + 1] = rscor[3 * q + 2] = 0.0;
+                        if (status) atomicOr(status, 1u);
+                    }
+                    continue;
+                }
+                const uint32_t nsnps = finish_counts<kSubsample>(T, lane, counts, mq);
+                uint32_t best = 0;
+                if (nsnps == 0) best = tiebreak_split(seed, t);            // stands in for :231
+                else actmask |= 1u << j;
+                if (lane == j) { my_q = mq; my_nsnps = nsnps; my_best = best; }
+            }
+            double score[3] = {0.001, 0.001, 0.001};                        // :232
+            uint32_t minrank = 0;
+            if (actmask) svd_scores4(&sh.T[0][0], slots, actmask, sv, lane, score, my_best, minrank);
+            if (lane < 4 && my_q >= 0) {
+                rscor[3 * my_q] = score[0]; rscor[3 * my_q + 1] = score[1]; rscor[3 * my_q + 2] = score[2];
+                rstat[my_q] = make_uint2(my_best, my_nsnps);                // :251, :264
+                if (minrank_out) minrank_out[my_q] = minrank;
+            }
+            __syncwarp();
+            if (lane == 0)
+                for (int j = 0; j < nq; ++j) mbar_arrive(&sh.empty[(ticket0 + (uint32_t)j) % kSlots]);
+        }
+    }
+}
+
+template <bool kSubsample, bool kShared>
+static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, uint32_t ntips, const uint4 *quartets,
+                                      int64_t m, uint64_t seed, double *d_rscor, uint2 *rstat, uint32_t *d_counts,
+                                      uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream)
+{
+    auto kern = resolve_mma_kernel<kSubsample, kShared, kNC, kNS>;
+    const size_t smem = sizeof(MmaShared<kNC, kNS>);
+    static SmemAttr attr;
+    cudaError_t e = attr.ensure(kern, smem);
+    if (e != cudaSuccess) return e;
+    const int64_t want = (m + kNC - 1) / kNC;
+    const unsigned grid = (unsigned)(want < num_sms ? want : num_sms);
+    const int64_t fv = g_mma_flush.load();
+    const uint32_t flush_every = (fv >= 1 && fv < (int64_t)kMmaFlushEvery) ? (uint32_t)fv : kMmaFlushEvery;
+    kern<<<grid, (kNC + kNS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank,
+                                                   d_status, flush_every);
+    ++g_launches;
+    g_last_kernel = kShared ? (kSubsample ? "tq::resolve_mma_kernel<sub, shared TMA ring>" : "tq::resolve_mma_kernel<full, shared TMA ring>")
+                            : (kSubsample ? "tq::resolve_mma_kernel<sub, cp.async rings>" : "tq::resolve_mma_kernel<full, cp.async rings>");
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips,
+                           const uint32_t *d_quartets, int64_t m, bool subsample, uint64_t seed,
+                           double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
+                           uint32_t *d_minrank, uint32_t *d_status, int num_sms,
+                           cudaStream_t stream)
+{
+    if (m == 0) return cudaSuccess;
+    const uint4 *planes = reinterpret_cast<const uint4 *>(d_planes);
+    const uint4 *quartets = reinterpret_cast<const uint4 *>(d_quartets);
+    uint2 *rstat = reinterpret_cast<uint2 *>(d_rstat);
+    // Variants of the same device code.  On tiny launches (C1: 495 quartets) a count -> score hand-off is pure latency, so
+    // the one-warp-per-quartet kernel runs; from 16 quartets per SM the tensor-core count kernel (profiles/tools/
+    // time_small.py, C2 matrix, M quartets/s fused / mma: 1 184 quartets 4.5 / 4.1, 2 368: 6.0 / 6.2, 4 736: 7.1 / 8.0,
+    // 37 888: 7.4 / 10.7).  Full mode with a dense quartet list goes to the tip-pair GEMM (tq_pairgemm.cu).
+    const int force = g_kernel_choice.load();
+    if (!subsample && (force == 5 || (force == 0 && pairgemm_applies(ntips, m, num_sms))))
+        return launch_resolve_pairgemm(plan, d_planes, ntips, d_quartets, m, seed, d_rscor, d_rstat, d_counts, d_minrank,
+                                       d_status, num_sms, stream);
+    const bool use_mma = force ? (force == 3 || force == 4 || force == 5) : (m >= (int64_t)num_sms * 16);
+    if (use_mma) {
+        const bool shared = force == 4 || (force != 3 && g_default_shared_ring.load() != 0);
+        if (shared)
+            return subsample ? launch_resolve_mma<true, true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
+                                                              d_counts, d_minrank, d_status, num_sms, stream)
+                             : launch_resolve_mma<false, true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
+                                                               d_counts, d_minrank, d_status, num_sms, stream);
+        return subsample ? launch_resolve_mma<true, false>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
+                                                           d_counts, d_minrank, d_status, num_sms, stream)
+                         : launch_resolve_mma<false, false>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
+                                                            d_counts, d_minrank, d_status, num_sms, stream);
+    }
+    g_last_kernel = subsample ? "tq::resolve_kernel<true>" : "tq::resolve_kernel<false>";
+    const size_t smem = sizeof(WarpScratch) * kWarps;
+    static SmemAttr attr_sub, attr_full;
+    cudaError_t e = subsample ? attr_sub.ensure(resolve_kernel<true>, smem) : attr_full.ensure(resolve_kernel<false>, smem);
+    if (e != cudaSuccess) return e;
+    const int64_t want = (m + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)num_sms * 4;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (subsample)
+        resolve_kernel<true><<<grid, kWarps * 32, smem, stream>>>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
+                                                                  d_counts, d_minrank, d_status);
+    else
+        resolve_kernel<false><<<grid, kWarps * 32, smem, stream>>>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
+                                                                   d_counts, d_minrank, d_status);
+    ++g_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace tq

@@ -120,8 +120,10 @@ struct __align__(16) SvdScratch4 {
 
 // Tbase: the CTA's slot array (256 counts per slot); slots: slot index of quartet j in byte j; actmask bit j: quartet j
 // is present and has SNPs.  Lane j < 4 receives the result of quartet j.
-__device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, uint32_t actmask, SvdScratch4 &sv, int lane,
-                                         double (&score_out)[3], uint32_t &best_out, uint32_t &minrank_out)
+// tptr(j): count tensor of quartet j (shared or global memory).
+template <class TPtr>
+__device__ __noinline__ void svd_scores4_impl(TPtr tptr, uint32_t actmask, SvdScratch4 &sv, int lane,
+                                              double (&score_out)[3], uint32_t &best_out, uint32_t &minrank_out)
 {
     const int m = lane >> 3, s = lane & 7;
 #pragma unroll 1
@@ -129,7 +131,7 @@ __device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, 
         const int mi = 4 * pass + m, qi = mi / 3, f = mi - 3 * qi;
         const bool act = (actmask >> qi) & 1u;
         if (!__any_sync(kFull, act)) continue;      // none of this pass's four matrices exists (fewer than four quartets)
-        const uint32_t *T = Tbase + ((slots >> (8 * qi)) & 0xFFu) * 256u;
+        const uint32_t *T = tptr(qi);
         __syncwarp();
         // this group's flattening (resolve_quartets.py:63,67-72), stored column-major; 32 of its 256 entries per lane
         double fro2 = 0.0;
@@ -344,6 +346,14 @@ __device__ __noinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, 
         minrank_out = (uint32_t)mr;
     }
     __syncwarp();
+}
+
+// Tbase: the CTA's slot array (256 counts per slot); slots: slot index of quartet j in byte j.
+__device__ __forceinline__ void svd_scores4(const uint32_t *Tbase, uint32_t slots, uint32_t actmask, SvdScratch4 &sv, int lane,
+                                            double (&score_out)[3], uint32_t &best_out, uint32_t &minrank_out)
+{
+    svd_scores4_impl([=](int qi) { return Tbase + ((slots >> (8 * qi)) & 0xFFu) * 256u; }, actmask, sv, lane, score_out,
+                     best_out, minrank_out);
 }
 
 // Zero-SNP quartets (reference :230-232): scores 0.001 and a split from a counter-based hash of (seed, tips) that the
