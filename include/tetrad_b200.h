@@ -215,15 +215,12 @@ int64_t tq_launch_count(void);
  * ("tq::resolve_mma_kernel<true>", ...); a static string, never NULL */
 const char *tq_last_kernel(void);
 
-/* Tuning / test hooks; process-wide, initialised from the environment (TQ_KERNEL, TQ_MMA_FLUSH, TQ_SHARED_RING).
+/* Tuning / test hooks; process-wide, initialised from the environment (TQ_KERNEL, TQ_MMA_FLUSH).
  *   "kernel"           0 = chosen by launch size and mode (default), 1 = one-warp-per-quartet POPC kernel,
- *                      3 = tensor-core (IMMA) count kernel with per-warp cp.async rings, 4 = the same with the CTA-shared
- *                      ring of TMA bulk copies, 5 = tip-pair GEMM on tcgen05.mma (full mode; subsample launches run 4)
- *   "shared_ring"      which staging the tensor-core count kernel uses when it is chosen by size: 1 (default) the
- *                      CTA-shared TMA ring, 0 per-warp cp.async rings
+ *                      3 = tensor-core (IMMA) count kernel, 5 = tip-pair GEMM on tcgen05.mma (full mode; a subsample
+ *                      launch runs 3)
  *   "mma_flush_every"  > 0: tile products between accumulator flushes of the tensor-core kernel
  *                      (default 16384; tests lower it to reach the flush path), 0 = default
- *   "pairgemm_desc_mode"  debugging aid of the tip-pair GEMM's shared-memory descriptors (0 = as documented)
  * Returns TQ_EINVAL for an unknown name or an out-of-range value. */
 int tq_set_option(const char *name, int64_t value);
 

@@ -63,7 +63,7 @@ def check_against_oracle(eng, oracle, db, quartets, sub, label):
     return worst
 
 
-@pytest.mark.parametrize("kernel_name", ["fused", "mma", "mma_shared", "pairgemm"])
+@pytest.mark.parametrize("kernel_name", ["fused", "mma", "pairgemm"])
 @pytest.mark.parametrize("sub", [True, False])
 def test_c1_exhaustive(tb, oracle, kernel_name, sub):
     """C1: 12 tips, 5 000 loci, 20 000 SNPs, all 495 quartets -- the reference's own CPU-runnable case."""
@@ -88,9 +88,8 @@ def test_c2_sampled(tb, oracle, sub):
     quartets = sampled_quartets("C2", 2000)
     eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
     try:
-        for name in ("mma", "mma_shared"):
-            _lib.set_kernel(name)
-            check_against_oracle(eng, oracle, db, quartets, sub, f"C2_{'sub' if sub else 'full'}_{name}")
+        _lib.set_kernel("mma")
+        check_against_oracle(eng, oracle, db, quartets, sub, f"C2_{'sub' if sub else 'full'}_mma")
     finally:
         _lib.set_kernel("auto")
         eng.close()
@@ -126,10 +125,10 @@ def test_large_shapes_sampled(tb, oracle, name, count, modes):
     db = config(name)
     quartets = sampled_quartets(name, count)
     eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
-    _lib.set_kernel("mma_shared")
+    _lib.set_kernel("mma")
     try:
         for sub in modes:
-            check_against_oracle(eng, oracle, db, quartets, sub, f"{name}_{'sub' if sub else 'full'}_mma_shared")
+            check_against_oracle(eng, oracle, db, quartets, sub, f"{name}_{'sub' if sub else 'full'}_mma")
     finally:
         _lib.set_kernel("auto")
         eng.close()

@@ -180,10 +180,10 @@ def check(code: int) -> None:
         raise TetradB200Error(code, load().tq_last_error().decode("utf-8", "replace"))
 
 
-KERNELS = {"auto": 0, "fused": 1, "mma": 3, "mma_shared": 4, "pairgemm": 5}
+KERNELS = {"auto": 0, "fused": 1, "mma": 3, "pairgemm": 5}
 
 
 def set_kernel(name: str) -> None:
-    """Force a resolve-kernel variant ("fused", "mma" = tensor-core count with per-warp cp.async rings, "mma_shared" = with
-    the CTA-shared TMA ring, "pairgemm" = tip-pair GEMM for full mode) or go back to the size rule ("auto")."""
+    """Force a resolve-kernel variant ("fused", "mma" = tensor-core count kernel, "pairgemm" = tip-pair GEMM on tcgen05
+    for full mode) or go back to the size rule ("auto")."""
     check(load().tq_set_option(b"kernel", KERNELS[name]))

@@ -102,9 +102,13 @@ struct tq_plan {
     tq::PlanDev dev{};
 };
 
+static constexpr int kHostChunks = 4;     // tq_resolve_host: result chunks copied back beside the next chunk's kernel
+
 struct tq_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // device -> host copies of finished result chunks
+    cudaEvent_t chunk_done[kHostChunks] = {};
     // cached replicate state
     tq_plan *plan = nullptr;
     const void *key_arr = nullptr, *key_loc = nullptr;
@@ -131,19 +135,9 @@ int tq_set_option(const char *name, int64_t value)
 {
     if (!name) return fail(TQ_EINVAL, "tq_set_option: null name");
     if (!strcmp(name, "kernel")) {
-        if (value < 0 || value > 5 || value == 2)
-            return fail(TQ_EINVAL, "tq_set_option: kernel must be 0 (auto), 1 (fused), 3 (mma), 4 (mma_shared) or 5 (pairgemm)");
+        if (value != 0 && value != 1 && value != 3 && value != 5)
+            return fail(TQ_EINVAL, "tq_set_option: kernel must be 0 (auto), 1 (fused), 3 (mma) or 5 (pairgemm)");
         tq::g_kernel_choice = (int)value;
-        return TQ_OK;
-    }
-    if (!strcmp(name, "shared_ring")) {
-        if (value < 0 || value > 1) return fail(TQ_EINVAL, "tq_set_option: shared_ring must be 0 or 1");
-        tq::g_default_shared_ring = (int)value;
-        return TQ_OK;
-    }
-    if (!strcmp(name, "pairgemm_desc_mode")) {
-        if (value < 0 || value > 1) return fail(TQ_EINVAL, "tq_set_option: pairgemm_desc_mode must be 0 or 1");
-        tq::g_pairgemm_desc_mode = (int)value;
         return TQ_OK;
     }
     if (!strcmp(name, "mma_flush_every")) {
@@ -481,7 +475,9 @@ int tq_ctx_create(int device, tq_ctx **out)
     c->device = device;
     DeviceGuard guard(device);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete c; return fail(TQ_ECUDA, "tq_ctx_create: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < kHostChunks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->chunk_done[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { tq_ctx_destroy(c); return fail(TQ_ECUDA, "tq_ctx_create: %s", cudaGetErrorString(e)); }
     *out = c;
     return TQ_OK;
 }
@@ -492,6 +488,9 @@ void tq_ctx_destroy(tq_ctx *c)
     DeviceGuard guard(c->device);
     if (c->plan) tq_plan_destroy(c->plan);
     cudaFree(c->d_tmparr); cudaFree(c->d_planes); cudaFree(c->d_quart); cudaFree(c->d_out);
+    for (int i = 0; i < kHostChunks; ++i)
+        if (c->chunk_done[i]) cudaEventDestroy(c->chunk_done[i]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -569,22 +568,29 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
     if ((rc = grow(&c->d_out, &c->cap_out, out_bytes)) != TQ_OK) return rc;
     char *o = static_cast<char *>(c->d_out);
     TQ_CUDA(cudaMemsetAsync(o + o_status, 0, 16, c->stream));
-    if ((rc = tq_resolve(c->plan, (const uint32_t *)c->d_planes, ntips, (const uint32_t *)c->d_quart, m, subsample,
-                         seed, (double *)(o + o_scor), (uint32_t *)(o + o_stat),
-                         h_counts ? (uint32_t *)(o + o_counts) : nullptr, (uint32_t *)(o + o_mr),
-                         (uint32_t *)(o + o_status), c->stream)) != TQ_OK)
-        return rc;
-    TQ_CUDA(cudaMemcpyAsync(h_rscor, o + o_scor, (size_t)m * 24, cudaMemcpyDeviceToHost, c->stream));
-    TQ_CUDA(cudaMemcpyAsync(h_rstat, o + o_stat, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
-    c->last_d2h += m * 32;
-    if (h_minrank) {
-        TQ_CUDA(cudaMemcpyAsync(h_minrank, o + o_mr, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
-        c->last_d2h += m * 4;
+    // Subsample mode, large lists: the list is resolved in kHostChunks launches and every chunk's results travel back
+    // on the copy stream while the next chunk is being resolved, so only the last chunk's copy is exposed.  (Full mode
+    // keeps one launch: the tip-pair GEMM is chosen by the density of the WHOLE list.)
+    const int nch = (subsample && m >= 65536) ? kHostChunks : 1;
+    for (int ch = 0; ch < nch; ++ch) {
+        const int64_t lo = m * ch / nch, hi = m * (ch + 1) / nch;
+        if ((rc = tq_resolve(c->plan, (const uint32_t *)c->d_planes, ntips, (const uint32_t *)c->d_quart + 4 * lo, hi - lo,
+                             subsample, seed, (double *)(o + o_scor) + 3 * lo, (uint32_t *)(o + o_stat) + 2 * lo,
+                             h_counts ? (uint32_t *)(o + o_counts) + 256 * lo : nullptr, (uint32_t *)(o + o_mr) + lo,
+                             (uint32_t *)(o + o_status), c->stream)) != TQ_OK)
+            return rc;
+        TQ_CUDA(cudaEventRecord(c->chunk_done[ch], c->stream));
     }
-    if (h_counts) {
-        TQ_CUDA(cudaMemcpyAsync(h_counts, o + o_counts, (size_t)m * 1024, cudaMemcpyDeviceToHost, c->stream));
-        c->last_d2h += m * 1024;
+    for (int ch = 0; ch < nch; ++ch) {
+        const int64_t lo = m * ch / nch, hi = m * (ch + 1) / nch, n = hi - lo;
+        TQ_CUDA(cudaStreamWaitEvent(c->copy_stream, c->chunk_done[ch], 0));
+        TQ_CUDA(cudaMemcpyAsync(h_rscor + 3 * lo, o + o_scor + lo * 24, (size_t)n * 24, cudaMemcpyDeviceToHost, c->copy_stream));
+        TQ_CUDA(cudaMemcpyAsync(h_rstat + 2 * lo, o + o_stat + lo * 8, (size_t)n * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (h_minrank) TQ_CUDA(cudaMemcpyAsync(h_minrank + lo, o + o_mr + lo * 4, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (h_counts) TQ_CUDA(cudaMemcpyAsync(h_counts + 256 * lo, o + o_counts + lo * 1024, (size_t)n * 1024, cudaMemcpyDeviceToHost, c->copy_stream));
     }
+    c->last_d2h += m * 32 + (h_minrank ? m * 4 : 0) + (h_counts ? m * 1024 : 0);
+    TQ_CUDA(cudaStreamSynchronize(c->copy_stream));
     TQ_CUDA(cudaStreamSynchronize(c->stream));
     return TQ_OK;
 }

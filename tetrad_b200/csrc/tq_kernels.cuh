@@ -55,10 +55,7 @@ void sample_ranks_host(int64_t start, int64_t m, uint32_t ntips, uint64_t key, i
 cudaError_t run_microbench(int kind, double *result);
 
 extern std::atomic<int64_t> g_launches;      // kernels launched by this library since load
-extern std::atomic<int> g_kernel_choice;          // 0 by launch size, 1 fused POPC, 3 tensor-core count (cp.async rings),
-                                                  // 4 tensor-core count (CTA-shared TMA ring), 5 tip-pair GEMM (full mode)
-extern std::atomic<int> g_default_shared_ring;    // staging of the tensor-core count kernel when chosen by size: 1 shared TMA ring
-extern std::atomic<int> g_pairgemm_desc_mode;     // debugging: 1 swaps the descriptor offsets of the tip-pair GEMM
+extern std::atomic<int> g_kernel_choice;          // 0 by launch size and mode, 1 fused POPC, 3 tensor-core count, 5 tip-pair GEMM (full mode)
 extern std::atomic<int64_t> g_mma_flush;          // > 0: tile products between accumulator flushes of the tensor-core kernel (tests)
 extern std::atomic<const char *> g_last_kernel;   // name of the resolve kernel variant launched last
 

@@ -80,7 +80,6 @@ struct PairGemmArgs {
     const uint32_t *cell_count;
     const uint2 *entries;          // (quartet index, local row pair << 8 | local column pair), bucketed by cell
     uint32_t *counts;              // [m][256]
-    uint32_t desc_mode;            // debugging: 1 swaps the two descriptor offsets
 };
 
 // pair numbering: row pairs by (t1, t0): rp = t1 (t1 - 1) / 2 + t0;  column pairs by (t2, t3): cp = off(t2) + t3 - t2 - 1
@@ -250,8 +249,9 @@ pair_gemm_kernel(PairGemmArgs args, int group)
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------ MMA issuer ------------------------------
-        const uint32_t a_lbo = args.desc_mode ? 128u : 128u * 16u, a_sbo = args.desc_mode ? 128u * 16u : 128u;
-        const uint32_t b_lbo = args.desc_mode ? 128u : 256u * 16u, b_sbo = args.desc_mode ? 256u * 16u : 128u;
+        // K-major, no swizzle: the two 16-byte K chunks of a K = 32 step are rows x 16 B apart (leading byte offset), the
+        // 8-row core matrices 128 B apart (stride byte offset)
+        const uint32_t a_lbo = 128u * 16u, b_lbo = 256u * 16u, a_sbo = 128u, b_sbo = 128u;
         uint32_t it = 0, tcount = 0;
         for (uint32_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x, ++tcount) {
             const uint32_t buf = tcount & 1u;
@@ -369,8 +369,6 @@ score_counts_kernel(const uint32_t *__restrict__ counts, const uint4 *__restrict
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-std::atomic<int> g_pairgemm_desc_mode{0};
-
 bool pairgemm_applies(int64_t ntips, int64_t m, int num_sms)
 {
     if (ntips < 5 || ntips > 2048 || m < (int64_t)num_sms * 16) return false;
@@ -466,7 +464,7 @@ cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_plane
         PairGemmArgs args;
         args.planes = d_planes; args.row_u4 = plan.row_u4; args.ntips = n; args.npairs = np; args.ntc = ntc;
         args.tile_list = tile_list; args.tile_range = tile_range; args.cell_off = cell_off; args.cell_count = cell_count;
-        args.entries = entries; args.counts = counts; args.desc_mode = (uint32_t)g_pairgemm_desc_mode.load();
+        args.entries = entries; args.counts = counts;
         // group g: GEMM on the caller's stream, its scores on the side stream behind an event -- beside the GEMM of g + 1
         cudaEvent_t ev[kGroups + 1];
         for (int g = 0; g <= kGroups; ++g) PG_CHECK(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));

@@ -3,12 +3,13 @@
 //   resolve_mma_kernel     the kernel large launches run.  8 count warps + 8 score warps per CTA, one CTA per SM.
 //                          Count warps: stage 1 selects one SNP per locus (running OR over the rank chunks of the four
 //                          tip rows), stage 2 forms the 256 site-pattern counts of every 1024-locus tile on the integer
-//                          tensor cores (IMMA.16832.U8.U8 on bit planes unpacked by one LOP3 per four loci).  The tip rows
-//                          reach shared memory either through a per-warp cp.async ring (kShared = false) or -- the eight
-//                          count warps of a CTA work on eight CONSECUTIVE quartets, which share most of their tips --
-//                          through ONE CTA-wide ring of TMA bulk copies that holds every distinct row of the batch once
-//                          (kShared = true: 11 rows instead of 32 per batch of an exhaustive list).  Score warps take four
-//                          finished quartets at a time through the FP64 QR + Jacobi of tq_svd.cuh.
+//                          tensor cores (IMMA.16832.U8.U8 on bit planes unpacked by one LOP3 per four loci); the tip rows
+//                          reach shared memory through a per-warp cp.async ring.  Score warps take four finished quartets
+//                          at a time through the FP64 QR + Jacobi of tq_svd.cuh.  (A CTA-wide ring of TMA bulk copies that
+//                          holds every distinct row of eight consecutive quartets once was built and measured in round 2:
+//                          correct, but half as fast -- sharing one ring lock-steps the count warps, so their IMMA and load
+//                          phases stop overlapping, and four stages do not cover a bulk copy's latency;
+//                          profiles/dropped/r02_shared_tma_ring.md.)
 //   resolve_kernel         one warp per quartet, counts by AND + POPC with the packed counters in tensor memory
 //                          (tcgen05.alloc / ld / st), scores by the same tq_svd.cuh code: what small launches run (a
 //                          count -> score hand-off is pure latency when there are fewer quartets than warps).
@@ -42,13 +43,13 @@ namespace tq {
 std::atomic<int64_t> g_launches{0};
 std::atomic<const char *> g_last_kernel{"none"};
 // Kernel choice and test hooks (tq_set_option in the C ABI; the environment gives the initial values).
-//   g_kernel_choice: 0 = by launch size, 1 = fused (one warp per quartet, POPC), 3 = tensor-core count, per-warp cp.async rings,
-//                    4 = tensor-core count, CTA-shared TMA ring, 5 = tip-pair GEMM (full mode only)
+//   g_kernel_choice: 0 = by launch size and mode, 1 = fused (one warp per quartet, POPC), 3 = tensor-core count,
+//                    5 = tip-pair GEMM (full mode only; subsample launches run 3)
 static int initial_kernel_choice()
 {
     const char *e = getenv("TQ_KERNEL");
     if (!e) return 0;
-    return !strcmp(e, "fused") ? 1 : !strcmp(e, "mma") ? 3 : !strcmp(e, "mma_shared") ? 4 : !strcmp(e, "pairgemm") ? 5 : 0;
+    return !strcmp(e, "fused") ? 1 : !strcmp(e, "mma") ? 3 : !strcmp(e, "pairgemm") ? 5 : 0;
 }
 static int64_t initial_mma_flush()
 {
@@ -57,8 +58,6 @@ static int64_t initial_mma_flush()
 }
 std::atomic<int> g_kernel_choice{initial_kernel_choice()};
 std::atomic<int64_t> g_mma_flush{initial_mma_flush()};
-// 1: large launches stage the tip rows through the CTA-shared TMA ring; 0: through per-warp cp.async rings
-std::atomic<int> g_default_shared_ring{getenv("TQ_SHARED_RING") ? atoi(getenv("TQ_SHARED_RING")) : 1};
 
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 static constexpr int kWarps = 4;                 // warps (= quartets in flight) per CTA of the fused kernel
@@ -569,60 +568,29 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
     flush_mma(acc, T, lane);
 }
 
-// ------------------------------------------------------------------------------------------
-// CTA-shared ring (kShared).  The NC count warps of a CTA always work on NC CONSECUTIVE quartets ("a batch").  In a
-// lexicographic list consecutive quartets differ in their last tip only, so a batch of 8 touches 11 distinct tip rows,
-// not 32 (a sorted random sample: ~20).  The rows of the batch are deduplicated (32 tip ids, one per lane:
-// __match_any_sync) and every DISTINCT row's rank chunk is brought in ONCE per stage by a TMA bulk copy
-// (cp.async.bulk, 512 B per row and stage) that completes on the stage's mbarrier; a stage is a slot of up to 32 rows
-// (16 KB), the ring has kMStages slots.  No warp is a producer: the count warp that finishes a stage LAST (one
-// shared-memory atomic per warp and stage) re-arms the slot and issues the copies of the stage kMStages ahead -- which
-// may already belong to the next batch, so the stream never drains between batches.  The count warps issue no LDGSTS,
-// compute no global addresses, and L2 -> SM traffic drops by the sharing factor.
-// ------------------------------------------------------------------------------------------
-static constexpr int kSlotRows = 4 * kNC;            // rows a stage can hold (no sharing at all: 4 per quartet)
-
 struct __align__(16) WsSlotMeta { long long q; uint4 tips; };   // hand-off slot: quartet index (or -1 - q: bad tips) and tips
 
-struct BatchRows {                // per-lane view of a batch's distinct rows (identical in every count warp)
-    uint32_t nd;                  // distinct rows of the batch
-    const uint4 *row;             // lane i < nd: start of distinct row i in global memory
-    uint32_t off[4];              // uint4 offset, inside a stage, of THIS lane's word of THIS warp's four tips
-};
-
-// tips of quartet (lane / 4) of the batch, tip (lane % 4); out-of-range / missing quartets read row 0 (never published)
-__device__ __forceinline__ BatchRows dedupe_batch(const uint4 *__restrict__ planes, uint32_t row_u4, uint32_t my_tip, int lane, int c)
-{
-    const uint32_t same = __match_any_sync(kFull, my_tip);
-    const bool leader = (uint32_t)(__ffs(same) - 1) == (uint32_t)lane;
-    const uint32_t leaders = __ballot_sync(kFull, leader);
-    const uint32_t my_slot = __popc(leaders & ((1u << (__ffs(same) - 1)) - 1u));       // rank of my leader among the leaders
-    BatchRows br;
-    br.nd = __popc(leaders);
-    const int src = (lane < (int)br.nd) ? (int)__fns(leaders, 0, lane + 1) : 0;       // lane of the leader with slot == lane
-    const uint32_t tip = __shfl_sync(kFull, my_tip, src);
-    br.row = planes + (size_t)tip * row_u4;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) br.off[t] = __shfl_sync(kFull, my_slot, 4 * c + t) * 32u + (uint32_t)lane;
-    return br;
-}
-
+// ------------------------------------------------------------------------------------------
+// Warp-specialised kernel around the tensor-core count path.  A CTA has NC count warps and NS score warps.  The count
+// path has no XU bottleneck and plenty of independent work per warp, so few count warps keep the SM's integer pipes busy;
+// the FP64 Jacobi is bound by its own dependency chains, so half of the register file goes to score warps.  Hand-off
+// through a CTA-wide ring of NC + 4 NS slots of 256 counts: producers take one ticket, consumers four (one shared-memory
+// atomic each), slot = ticket % slots, one full / empty mbarrier pair per slot, so ANY score warp takes the next finished
+// quartets -- no fixed count -> score pairing (every wait traps after seconds instead of hanging).
+// ------------------------------------------------------------------------------------------
 template <int NC, int NS>
 struct __align__(16) MmaShared {
     static constexpr int kSlots = NC + 4 * NS;      // every count warp fills one slot, every score warp holds up to four
-    uint4 ring[NC][kMStages][4][32];                // per-warp rings; the CTA-shared ring uses the same 64 KB as
-                                                    // [kMStages][kSlotRows][32]
+    uint4 ring[NC][kMStages][4][32];                // per-warp cp.async rings
     uint32_t P[NC][16 * kPStride];
     uint32_t T[kSlots][256];
     WsSlotMeta meta[kSlots];
     SvdScratch4 svd[NS];
     unsigned long long full[kSlots], empty[kSlots];
-    unsigned long long ring_full[kMStages];         // CTA-shared ring: bulk-copy completion barrier of every stage
-    uint32_t ring_done[kMStages];                   // count warps that have finished reading the stage
     uint32_t produce, consume;
 };
 
-template <bool kSubsample, bool kShared, int NC, int NS>
+template <bool kSubsample, int NC, int NS>
 __global__ void __launch_bounds__((NC + NS) * 32, 1)
 resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntips,
                    const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
@@ -633,7 +601,6 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
     using Shared = MmaShared<NC, NS>;
     constexpr int kSlots = Shared::kSlots;
     static_assert(kSlots <= 256, "slot indices travel in one byte each");
-    static_assert(!kShared || NC == 8, "the batch deduplication maps one tip to one lane: 8 quartets x 4 tips");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared &sh = *reinterpret_cast<Shared *>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -641,7 +608,6 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
-        for (int s = 0; s < kMStages; ++s) { mbar_init(&sh.ring_full[s], 1); sh.ring_done[s] = 0u; }
         sh.produce = 0u; sh.consume = 0u;
         mbar_init_fence();
     }
@@ -660,137 +626,24 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
     if (warp < NC) {
         // ------------------------------ count warps ------------------------------
         const int c = warp;
-        const uint32_t nchunks = plan.row_u4 / kTileWords;
-        // CTA-shared ring state, the same sequence in every count warp: slot rs and phase parity ph of the next stage.
-        // The ring has RS = min(kMStages, nchunks) slots, so the stage RS ahead of a chunk of batch `it` belongs to
-        // batch it or it + 1, never further.
-        const uint32_t RS = nchunks < (uint32_t)kMStages ? nchunks : (uint32_t)kMStages;
-        uint32_t rs = 0u, ph = 0u;
-        uint32_t cur_nd = 0u, nxt_nd = 0u;
-        const uint4 *cur_row = planes, *nxt_row = planes;                     // lane i: distinct row i of the batch / the next one
-        uint32_t off0 = 0u, off1 = 0u, off2 = 0u, off3 = 0u;
-        auto load_rows = [&](int64_t it) -> BatchRows {                      // rows of this CTA's it-th batch
-            uint32_t tip = 0u;
-            if (it < my_batches) {
-                const int64_t qq = ((int64_t)blockIdx.x + it * gridDim.x) * NC + (lane >> 2);
-                if (qq < m) {
-                    const uint32_t *qt = reinterpret_cast<const uint32_t *>(quartets + qq);
-                    tip = __ldg(qt + (lane & 3));
-                    if (tip >= ntips) tip = 0u;
-                }
-            }
-            return dedupe_batch(planes, plan.row_u4, tip, lane, c);
-        };
-        // bulk copies of one stage: rank chunk `chunk` of the `nd` distinct rows `row` into ring slot `slot`
-        auto issue_stage = [&](uint32_t slot, uint32_t chunk, uint32_t nd, const uint4 *row) {
-            unsigned long long *bar = &sh.ring_full[slot];
-            if (lane == 0) mbar_arrive_expect_tx(bar, nd * 512u);
-            __syncwarp();
-            if (lane < (int)nd)
-                bulk_copy_g2s(smem_u32(&sh.ring[0][0][0][0]) + slot * (kSlotRows * 512u) + (uint32_t)lane * 512u,
-                              row + (size_t)chunk * kTileWords, 512u, bar);
-        };
-        if (kShared && my_batches > 0 && nchunks > 0) {
-            const BatchRows b0 = load_rows(0), b1 = load_rows(1);
-            cur_nd = b0.nd; cur_row = b0.row; off0 = b0.off[0]; off1 = b0.off[1]; off2 = b0.off[2]; off3 = b0.off[3];
-            nxt_nd = b1.nd; nxt_row = b1.row;
-            if (c == 0)                                    // prologue: the first RS stages of the stream (RS <= nchunks: batch 0)
-                for (uint32_t i = 0; i < RS; ++i) issue_stage(i, i, cur_nd, cur_row);
-        }
         for (int64_t it = 0; it < my_batches; ++it) {
             const int64_t q = ((int64_t)blockIdx.x + it * gridDim.x) * NC + c;
-            const bool present = q < m;
-            uint32_t ticket = 0, slot = 0;
-            uint32_t *T = nullptr;
-            uint4 t = make_uint4(0u, 0u, 0u, 0u);
-            bool bad = false;
-            if (present) {
-                if (lane == 0) ticket = atomicAdd(&sh.produce, 1u);
-                ticket = __shfl_sync(kFull, ticket, 0);
-                slot = ticket % kSlots;
-                mbar_wait(&sh.empty[slot], ((ticket / kSlots) & 1u) ^ 1u);   // slot free (passes at once on its first use)
-                T = sh.T[slot];
-                t = __ldg(quartets + q);
-                bad = t.x >= ntips || t.y >= ntips || t.z >= ntips || t.w >= ntips;
+            if (q >= m) break;                                               // the last batch may be short
+            uint32_t ticket = 0;
+            if (lane == 0) ticket = atomicAdd(&sh.produce, 1u);
+            ticket = __shfl_sync(kFull, ticket, 0);
+            const uint32_t slot = ticket % kSlots;
+            mbar_wait(&sh.empty[slot], ((ticket / kSlots) & 1u) ^ 1u);       // slot free (passes at once on its first use)
+            uint32_t *T = sh.T[slot];
+            const uint4 t = __ldg(quartets + q);
+            const bool bad = t.x >= ntips || t.y >= ntips || t.z >= ntips || t.w >= ntips;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
-                __syncwarp();
-            }
-            if constexpr (!kShared) {
-                if (present && !bad)
-                    count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every);
-            } else if (nchunks > 0) {     // (kShared)
-                // ---- stage 1 from the CTA-shared ring; every count warp walks the same stages, present or not ----
-                const bool work = present && !bad;
-                int acc[kScales][2][4];
-#pragma unroll
-                for (int v = 0; v < kScales; ++v)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[v][h][i] = 0;
-                const MmaLanePtrs lp = mma_lane_ptrs(sh.P[c], lane);
-                uint32_t pending = 0;
-                const uint4 *ringbase = &sh.ring[0][0][0][0];
-                const bool more = it + 1 < my_batches;                 // the stream goes on into another batch
-                const int ntiles = plan.ntiles;
-                uint32_t Knext = ntiles > 0 ? __ldg(plan.tile_k) : 0u;
-                uint32_t u = 0;                                        // rank-chunk index along the rows
-                for (int tile = 0; tile < ntiles; ++tile) {
-                    const uint32_t K = Knext;
-                    if (tile + 1 < ntiles) Knext = __ldg(plan.tile_k + tile + 1);
-                    uint32_t taken = 0u;
-                    uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
-                    uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
-                    for (uint32_t k = 0; k < K; ++k, ++u) {
-                        mbar_wait_short(&sh.ring_full[rs], ph);        // the stage has landed
-                        const uint4 *st = ringbase + rs * (kSlotRows * 32);
-                        const uint4 a = st[off0], b = st[off1], cc = st[off2], d = st[off3];
-                        __syncwarp();                                  // every lane's reads of the stage have been issued
-                        uint32_t last = 0u;
-                        if (lane == 0) {
-                            uint32_t old;
-                            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;\n"
-                                         : "=r"(old) : "r"(smem_u32(&sh.ring_done[rs])) : "memory");
-                            last = old == (uint32_t)(NC - 1);
-                            if (last) sh.ring_done[rs] = 0u;           // re-armed before the copies below can complete
-                        }
-                        last = __shfl_sync(kFull, last, 0);
-                        if (last) {                                    // this warp read the stage last: refill its slot
-                            const uint32_t nu = u + RS;                // with the stage RS ahead in the stream
-                            if (nu < nchunks) issue_stage(rs, nu, cur_nd, cur_row);
-                            else if (more) issue_stage(rs, nu - nchunks, nxt_nd, nxt_row);
-                        }
-                        if (++rs == RS) { rs = 0u; ph ^= 1u; }
-                        if (work) {
-                            if (kSubsample) {
-                                select_chunk(a, b, cc, d, taken, MA, MB, MC, MD);
-                            } else {
-                                const uint32_t A[4] = {a.x, a.y, a.z, a.w}, B[4] = {b.x, b.y, b.z, b.w};
-                                const uint32_t C[4] = {cc.x, cc.y, cc.z, cc.w}, D[4] = {d.x, d.y, d.z, d.w};
-                                count_tile_mma(A, B, C, D, lp, acc);
-                                if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
-                            }
-                        }
-                    }
-                    if (kSubsample && work) {
-                        finish_tile_planes(taken, MA, MB, MC, MD);
-                        count_tile_mma(MA, MB, MC, MD, lp, acc);
-                        if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
-                    }
-                }
-                if (work) flush_mma(acc, T, lane);
-                {   // the next batch becomes the current one; look one further ahead
-                    const BatchRows b1 = load_rows(it + 1), b2 = load_rows(it + 2);
-                    cur_nd = b1.nd; cur_row = b1.row; off0 = b1.off[0]; off1 = b1.off[1]; off2 = b1.off[2]; off3 = b1.off[3];
-                    nxt_nd = b2.nd; nxt_row = b2.row;
-                }
-            }
-            if (present) {
-                if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.full[slot]);
-            }
+            for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
+            __syncwarp();
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every);
+            if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.full[slot]);
         }
     } else {
         // ------------------------------ score warps ------------------------------
@@ -843,12 +696,12 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
     }
 }
 
-template <bool kSubsample, bool kShared>
+template <bool kSubsample>
 static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, uint32_t ntips, const uint4 *quartets,
                                       int64_t m, uint64_t seed, double *d_rscor, uint2 *rstat, uint32_t *d_counts,
                                       uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream)
 {
-    auto kern = resolve_mma_kernel<kSubsample, kShared, kNC, kNS>;
+    auto kern = resolve_mma_kernel<kSubsample, kNC, kNS>;
     const size_t smem = sizeof(MmaShared<kNC, kNS>);
     static SmemAttr attr;
     cudaError_t e = attr.ensure(kern, smem);
@@ -860,8 +713,7 @@ static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, 
     kern<<<grid, (kNC + kNS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank,
                                                    d_status, flush_every);
     ++g_launches;
-    g_last_kernel = kShared ? (kSubsample ? "tq::resolve_mma_kernel<sub, shared TMA ring>" : "tq::resolve_mma_kernel<full, shared TMA ring>")
-                            : (kSubsample ? "tq::resolve_mma_kernel<sub, cp.async rings>" : "tq::resolve_mma_kernel<full, cp.async rings>");
+    g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
     return cudaGetLastError();
 }
 
@@ -883,19 +735,12 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     if (!subsample && (force == 5 || (force == 0 && pairgemm_applies(ntips, m, num_sms))))
         return launch_resolve_pairgemm(plan, d_planes, ntips, d_quartets, m, seed, d_rscor, d_rstat, d_counts, d_minrank,
                                        d_status, num_sms, stream);
-    const bool use_mma = force ? (force == 3 || force == 4 || force == 5) : (m >= (int64_t)num_sms * 16);
-    if (use_mma) {
-        const bool shared = force == 4 || (force != 3 && g_default_shared_ring.load() != 0);
-        if (shared)
-            return subsample ? launch_resolve_mma<true, true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
-                                                              d_counts, d_minrank, d_status, num_sms, stream)
-                             : launch_resolve_mma<false, true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
-                                                               d_counts, d_minrank, d_status, num_sms, stream);
-        return subsample ? launch_resolve_mma<true, false>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
-                                                           d_counts, d_minrank, d_status, num_sms, stream)
-                         : launch_resolve_mma<false, false>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat,
-                                                            d_counts, d_minrank, d_status, num_sms, stream);
-    }
+    const bool use_mma = force ? (force == 3 || force == 5) : (m >= (int64_t)num_sms * 16);
+    if (use_mma)
+        return subsample ? launch_resolve_mma<true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat, d_counts,
+                                                    d_minrank, d_status, num_sms, stream)
+                         : launch_resolve_mma<false>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat, d_counts,
+                                                     d_minrank, d_status, num_sms, stream);
     g_last_kernel = subsample ? "tq::resolve_kernel<true>" : "tq::resolve_kernel<false>";
     const size_t smem = sizeof(WarpScratch) * kWarps;
     static SmemAttr attr_sub, attr_full;

@@ -62,6 +62,30 @@ def upload(array: np.ndarray, device):
     return t
 
 
+_PINNED_POOL: list = []
+
+
+def _pinned_array(shape, dtype):
+    """Result array backed by page-locked memory (device -> host copies into it are asynchronous DMA, not staged
+    through a driver buffer).  The backing tensors are pooled: one is reused once the arrays handed out from it have been
+    dropped by the caller (the ndarray keeps its tensor alive, so the tensor's reference count tells)."""
+    import sys
+    import torch
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    chosen = None
+    for t in _PINNED_POOL:
+        if nbytes <= t.numel() <= 2 * nbytes + 4096 and sys.getrefcount(t) <= 3:      # pool, loop variable, argument
+            chosen = t
+            break
+    if chosen is None:
+        chosen = torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True)
+        _PINNED_POOL.append(chosen)
+        if len(_PINNED_POOL) > 16:
+            _PINNED_POOL.pop(0)
+    return chosen.numpy()[:nbytes].view(dtype).reshape(shape)
+
+
 def _as_locus(tmpmap: np.ndarray):
     """(array kept alive, pointer, element stride) of the locus-id column tmpmap[:, 0]."""
     tmpmap = np.asarray(tmpmap)
@@ -100,8 +124,8 @@ def new_infer_resolved_quartets(tmparr: np.ndarray, tmpmap: np.ndarray, quartets
     quartets_in = quartets
     quartets = np.ascontiguousarray(quartets, dtype=np.uint32).reshape(-1, 4)
     m = quartets.shape[0]
-    rscor = np.empty((m, 3), dtype=np.float64)          # every element is written by the call (or it raises)
-    rstat = np.empty((m, 2), dtype=np.uint32)
+    rscor = _pinned_array((m, 3), np.float64)           # every element is written by the call (or it raises)
+    rstat = _pinned_array((m, 2), np.uint32)
     counts = np.empty((m, 16, 16), dtype=np.uint32) if return_counts else None
     minrank = np.empty(m, dtype=np.uint32) if return_counts else None
     _lib.check(lib.tq_resolve_host(
