@@ -291,6 +291,33 @@ def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local
     return block, binding
 
 
+def pairgemm_tiles(quartets: np.ndarray, ntips: int) -> int:
+    """Tiles (8 row pairs x 16 column pairs) of the tip-pair GEMM that hold at least one quartet of the list
+    (the device planner's count, recomputed on the host for the roofline arithmetic; tq_pairgemm.cu)."""
+    q = quartets.astype(np.int64)
+    n = ntips
+    rp = q[:, 1] * (q[:, 1] - 1) // 2 + q[:, 0]
+    cp = q[:, 2] * (2 * n - 1 - q[:, 2]) // 2 + q[:, 3] - q[:, 2] - 1
+    npairs = n * (n - 1) // 2
+    ntc = (npairs + 15) // 16
+    return int(len(np.unique((rp // 8) * ntc + cp // 16)))
+
+
+def tensor_block(quartets, ntips, padded_cols, kern_ms):
+    """Tensor-core roofline of the full-mode GEMM: u8 MACs the launch executed (non-empty tiles x 128 x 256 x K)
+    against twice the measured dense bf16 peak (int8 runs at twice the bf16 rate; MEASURED_PEAKS.json)."""
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    bf16 = json.loads(peaks_path.read_text())["bf16_tflops"] if peaks_path.exists() else 1590.0
+    tiles = pairgemm_tiles(quartets, ntips)
+    executed = 2.0 * tiles * 128 * 256 * padded_cols
+    useful = 2.0 * len(quartets) * 256 * padded_cols
+    return {"bound": "tensor", "achieved": executed / (kern_ms * 1e-3) / 1e12, "peak": 2.0 * bf16, "unit": "TOP/s",
+            "frac": executed / (kern_ms * 1e-3) / 1e12 / (2.0 * bf16), "tiles": tiles, "useful_fraction_of_executed": useful / executed,
+            "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (u8 tcgen05.mma runs at twice the bf16 rate)" if peaks_path.exists()
+                           else "2 x fallback of B200_PROFILING.md",
+            "note": "the launch's duration also covers the planner and the FP64 scores that run beside the GEMM on a second stream"}
+
+
 def bench_static(config, world, rank, local, dev, lib, steps, warmup, subsample=True, e2e=True):
     """Replicate 0 of an exhaustive config resolved `steps` times against the resident packed matrix; quartet ranges
     sharded over the ranks, results gathered to rank 0 inside the step."""
@@ -396,8 +423,8 @@ def bench_replicates(config, world, rank, local, dev, lib, steps, warmup, sample
     # ---- value: device time of K replicates, draws taken before the region --------------------------------------
     ready = [pipe.draw(1000 + i, rng) for i in range(steps)]
     barrier(world, dev)
-    sampler = ClockSampler(local)
-    sampler.start()
+    clock_sampler = ClockSampler(local)
+    clock_sampler.start()
     launches0 = lib.tq_launch_count()
     wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -407,7 +434,7 @@ def bench_replicates(config, world, rank, local, dev, lib, steps, warmup, sample
     barrier(world, dev)
     wall = time.perf_counter() - wall0
     launches = lib.tq_launch_count() - launches0
-    clocks = sampler.result()
+    clocks = clock_sampler.result()
     total_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     ev = [p.events for p in preps]
     prepare_ms = statistics.mean(e["prepare_start"].elapsed_time(e["prepare_end"]) for e in ev[1:]) if steps > 1 else \
@@ -428,7 +455,7 @@ def bench_replicates(config, world, rank, local, dev, lib, steps, warmup, sample
     d2h = Q * 32 + Q * 16                                                          # results + quartet ids, rank 0
     res = dict(Q=Q, value=Q * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps, kern_ms=kern_ms,
                quartets_per_launch=-(-Q // world), launches=int(launches), ncols=int(info["ncols"]), info=info,
-               clocks=clocks, wall=wall, kernel=lib.tq_last_kernel().decode(), sampler=sampler,
+               clocks=clocks, wall=wall, kernel=lib.tq_last_kernel().decode(), sampler_name=sampler,
                replicate={"prepare_ms": prepare_ms, "resolve_ms": kern_ms, "gather_ms": gather_ms,
                           "note": "device time of one rank's share of a replicate (CUDA events, rank 0): bootstrap column "
                                   "orders + planes of this rank's tip rows + all-gather + unranking | resolve of Q/N "
@@ -471,6 +498,8 @@ def run_ours(args):
         fm = bench_static("C2", world, rank, local, dev, lib, 5, 3, subsample=False, e2e=False)
         roof, bind = roofline_block("C2", fm["ncols"], fm["quartets_per_launch"], fm["kern_ms"], fm["info"], lib, local,
                                     subsample=False, kernel=fm["kernel"])
+        if "pair_gemm" in fm["kernel"]:
+            roof["tensor"] = tensor_block(fm["quartets"], synth.CONFIGS["C2"]["ntips"], fm["info"]["padded_cols"], fm["kern_ms"])
         extra["full_mode"] = {"config": describe("C2", subsample=False), "value": fm["value"], "ms_per_step": fm["ms_per_step"],
                               "roofline": roof, "binding": bind,
                               "note": "subsample_snps=False (full_chunk_to_matrices, the CLI's default mode) at the C2 shape"}
@@ -498,8 +527,8 @@ def run_ours(args):
                             (", bootstrap planes packed by tip-row shares + NCCL all-gather" if replicate_mode and world > 1 else ""),
              "quartets_per_step": res["Q"]}
     if replicate_mode:
-        setup["quartet_sampler"] = res["sampler"] + (" (keyed permutation on the device, one 63-bit draw per replicate)"
-                                                      if res["sampler"] == "device" else " (the reference's rng.choice on the host)")
+        setup["quartet_sampler"] = res["sampler_name"] + (" (keyed permutation on the device, one 63-bit draw per replicate)"
+                                                           if res["sampler_name"] == "device" else " (the reference's rng.choice on the host)")
     line = {
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": res["ms_per_step"], "higher_is_better": True,

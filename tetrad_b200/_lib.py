@@ -165,11 +165,12 @@ def load():
     """Load (never build) the shared library; raise if it is not there."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
+        path = Path(os.environ.get("TETRAD_B200_LIB", LIB_PATH))      # a variant build (measurements only)
+        if not path.exists():
             raise RuntimeError(
-                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(the CUDA extension is the only implementation; there is no CPU fallback)")
-        lib = ctypes.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else 0)
+        lib = ctypes.CDLL(str(path), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else 0)
         _declare(lib)
         _lib = lib
     return _lib

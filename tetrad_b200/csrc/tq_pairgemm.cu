@@ -20,12 +20,14 @@
 //   producers   12 warps, thread = one operand row (pair, ab): two 4-byte plane loads, one AND, and the 32 columns of
 //               the word become 32 bytes {0, 1} -- (x >> v) & 0x01010101 for v = 0..7 -- written as two 16-byte K chunks
 //               into the stage's K-major core-matrix layout (no swizzle: 8 rows x 16 B = one 128-byte core matrix)
-//   MMA         one thread issues 4 MMAs per stage (kKW = 4 words), tcgen05.commit releases the stage / publishes the tile
+//   MMA         one thread issues 8 MMAs per stage (kKW = 8 words), tcgen05.commit releases the stage / publishes the tile
 //   epilogue    4 warps (one per tensor-memory lane quadrant) read the wanted 16 x 16 blocks with tcgen05.ld and write the
 //               quartet's 256 counts (1 KB) to global memory; two accumulator buffers (2 x 256 TMEM columns) overlap the
 //               epilogue of tile i with the main loop of tile i + 1
-//   scores      score_counts_kernel (the same svd_scores4 as every other kernel) on a second stream, one group of tiles
-//               behind the GEMM: its CTAs (6 warps, FP64) fit beside a GEMM CTA on the SM
+//   scores      score_counts_kernel (the same svd_scores4 as every other kernel) after the GEMM, 16 warps per SM.  (Running
+//               it beside the GEMM on a second stream, one group of tiles behind, was measured first: 6 score warps fit
+//               next to a GEMM CTA, and the pair took as long as one after the other -- 20.8 ms against 10.8 + 12.5 under
+//               ncu -- because both live off the same issue slots; alone, each gets the whole SM.)
 //
 // Exactness: products are 0/1, accumulation is s32, K < 2^31 columns: counts are exact integers, bit-identical to the
 // other kernels'.  Applies when the list holds >= 30 % of all C(n,4) quartets (exhaustive lists in practice; a sparse
@@ -43,18 +45,17 @@ namespace tq {
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 static constexpr int kRP = 8;                     // row pairs per tile    -> M = 128
 static constexpr int kCP = 16;                    // column pairs per tile -> N = 256
-static constexpr int kKW = 4;                     // plane words per stage -> 4 MMAs of K = 32 bytes
-static constexpr int kGStages = 3;
+static constexpr int kKW = 8;                     // plane words per stage -> 8 MMAs of K = 32 bytes (96 KB of operands:
+static constexpr int kGStages = 2;                // the per-stage wait / fence / arrive is paid once per 256 columns)
 static constexpr int kProdWarps = 12;             // 384 producer threads = 128 A rows + 256 B rows
 static constexpr int kMmaWarp = kProdWarps;       // warp 12
                                                   // warps 13..16: epilogue (their index % 4 covers the four TMEM lane quadrants)
 static constexpr int kGemmThreads = (kProdWarps + 5) * 32;
-static constexpr uint32_t kABytes = kKW * 2 * 128 * 16;      // 16 KB: [word][K chunk][row][16 B]
-static constexpr uint32_t kBBytes = kKW * 2 * 256 * 16;      // 32 KB
+static constexpr uint32_t kABytes = kKW * 2 * 128 * 16;      // 32 KB: [word][K chunk][row][16 B]
+static constexpr uint32_t kBBytes = kKW * 2 * 256 * 16;      // 64 KB
 static constexpr uint32_t kStageBytes = kABytes + kBBytes;
 static constexpr uint32_t kTmemColsGemm = 512;               // two accumulators of 256 columns
-static constexpr int kScoreWarps = 6;
-static constexpr int kGroups = 4;                            // tile groups: scores of group g run beside the GEMM of group g + 1
+static constexpr int kScoreWarps = 16;                       // 512 threads x 128 registers = the SM's register file
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 at bit 4, a/b_format U8 = 0, K-major both,
 // n_dim = N >> 3 at bit 17, m_dim = M >> 4 at bit 24
@@ -75,7 +76,7 @@ struct PairGemmArgs {
     uint32_t npairs;               // n (n - 1) / 2
     uint32_t ntc;                  // column tiles per tile row
     const uint32_t *tile_list;     // non-empty cells, ascending
-    const uint32_t *tile_range;    // [kGroups + 1] tile index boundaries of the groups
+    const uint32_t *ntiles;        // number of non-empty cells (device: the planner's result)
     const uint32_t *cell_off;      // first entry of every cell
     const uint32_t *cell_count;
     const uint2 *entries;          // (quartet index, local row pair << 8 | local column pair), bucketed by cell
@@ -139,20 +140,13 @@ __global__ void __launch_bounds__(256) pg_flag_kernel(const uint32_t *__restrict
     if (i < ncells) flag[i] = cell_count[i] != 0u;
 }
 
-// tile_list[flag_scan[cell]] = cell for every non-empty cell (ascending), then the group boundaries
+// tile_list[flag_scan[cell]] = cell for every non-empty cell (ascending); ntiles[0] = their number
 __global__ void __launch_bounds__(256) pg_compact_kernel(const uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ flag_scan,
-                                                         uint32_t ncells, uint32_t grid, uint32_t *__restrict__ tile_list,
-                                                         uint32_t *__restrict__ tile_range)
+                                                         uint32_t ncells, uint32_t *__restrict__ tile_list, uint32_t *__restrict__ ntiles)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ncells && cell_count[i] != 0u) tile_list[flag_scan[i]] = i;
-    if (i == 0) {
-        // every tile costs the same, so a group is a whole number of waves of `grid` CTAs; the last one takes the rest
-        const uint32_t nact = flag_scan[ncells];
-        const uint32_t waves = (nact + grid - 1) / grid, per = (waves + kGroups - 1) / kGroups;
-        for (int g = 0; g <= kGroups; ++g) tile_range[g] = min(nact, (uint32_t)g * per * grid);
-        tile_range[kGroups] = nact;
-    }
+    if (i == 0) ntiles[0] = flag_scan[ncells];
 }
 
 __global__ void __launch_bounds__(256) pg_fill_kernel(const uint4 *__restrict__ quartets, int64_t m, uint32_t n, uint32_t ntc,
@@ -176,9 +170,52 @@ struct __align__(16) PairGemmShared {
     uint32_t tmem_base;
 };
 
-// (72 registers: a score CTA of 6 x 32 threads x 128 registers fits beside the 544 threads of this one)
-__global__ void __maxnreg__(72)
-pair_gemm_kernel(PairGemmArgs args, int group)
+// One producer thread = one operand row (pair, ab) of kRows (128: A, 256: B).  Per stage: kKW plane words -> kKW x 32 bytes
+// {0, 1}, two 16-byte K chunks per word at compile-time offsets from the row's slot in the stage.  Plane words are loaded
+// TWO stages ahead and right AFTER a stage's fence: fence.proxy.async is a full memory barrier (SASS MEMBAR.ALL.CTA), so
+// loads still in flight when it executes are waited for -- issued after it they have a whole stage of work to land.
+template <uint32_t kRows>
+__device__ __forceinline__ void produce_tile(const uint32_t *__restrict__ p0, const uint32_t *__restrict__ p1, uint32_t nst,
+                                             unsigned char *row_base, unsigned long long *full, unsigned long long *empty,
+                                             uint32_t &it, int lane)
+{
+    uint32_t x[kKW], na[kKW], nb[kKW];               // na & nb: the two planes of the next stage, ANDed when used
+#pragma unroll
+    for (int w = 0; w < kKW; ++w) {
+        x[w] = __ldg(p0 + 4 * w) & __ldg(p1 + 4 * w);
+        na[w] = nst > 1 ? __ldg(p0 + 4 * (kKW + w)) : 0u;
+        nb[w] = nst > 1 ? __ldg(p1 + 4 * (kKW + w)) : 0u;
+    }
+    for (uint32_t st = 0; st < nst; ++st, ++it) {
+        const uint32_t s = it % kGStages;
+        mbar_wait_short(&empty[s], ((it / kGStages) & 1u) ^ 1u);      // the MMAs that read this slot are done
+        unsigned char *base = row_base + s * kStageBytes;
+#pragma unroll
+        for (int w = 0; w < kKW; ++w) {
+            uint32_t o[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) o[v] = (x[w] >> v) & 0x01010101u;   // byte j of o[v] = column 8 j + v of the word
+            *reinterpret_cast<uint4 *>(base + w * kRows * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4 *>(base + w * kRows * 32 + kRows * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        fence_proxy_async_smem();                    // my stores are visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+#pragma unroll
+        for (int w = 0; w < kKW; ++w) x[w] = na[w] & nb[w];
+        if (st + 2 < nst) {
+            const uint32_t *q0 = p0 + (size_t)(st + 2) * kKW * 4, *q1 = p1 + (size_t)(st + 2) * kKW * 4;
+#pragma unroll
+            for (int w = 0; w < kKW; ++w) {
+                na[w] = __ldg(q0 + 4 * w);
+                nb[w] = __ldg(q1 + 4 * w);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+pair_gemm_kernel(PairGemmArgs args)
 {
     extern __shared__ __align__(1024) unsigned char pg_smem[];
     unsigned char *stages = pg_smem;
@@ -196,7 +233,7 @@ pair_gemm_kernel(PairGemmArgs args, int group)
     tcgen05_fence_after();
     const uint32_t tmem_base = sh.tmem_base;
 
-    const uint32_t tile_lo = args.tile_range[group], tile_hi = args.tile_range[group + 1];
+    const uint32_t tile_lo = 0u, tile_hi = args.ntiles[0];
     const uint32_t nst = args.row_u4 / kKW;                  // stages per tile (row_u4 is a multiple of 32)
     const uint32_t stage0 = smem_u32(stages);
 
@@ -205,7 +242,6 @@ pair_gemm_kernel(PairGemmArgs args, int group)
         const uint32_t row = threadIdx.x;                    // 0..127: A rows, 128..383: B rows
         const bool is_a = row < 128u;
         const uint32_t r = is_a ? row : row - 128u;          // row inside its operand
-        const uint32_t nrows = is_a ? 128u : 256u;
         const uint32_t dst0 = (is_a ? 0u : kABytes) + r * 16u;          // + word * nrows * 32 + chunk * nrows * 16
         uint32_t it = 0;                                      // stages produced so far (ring position)
         for (uint32_t tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
@@ -216,36 +252,8 @@ pair_gemm_kernel(PairGemmArgs args, int group)
             else { const uint32_t cp = tc * kCP + (r >> 4); pr = unrank_colpair(cp < args.npairs ? cp : args.npairs - 1, args.ntips); }
             const uint32_t *p0 = args.planes + (size_t)pr.x * args.row_u4 * 4 + ((r >> 2) & 3u);
             const uint32_t *p1 = args.planes + (size_t)pr.y * args.row_u4 * 4 + (r & 3u);
-            uint32_t nx[kKW];                                 // the stage after the one being expanded, already loaded
-#pragma unroll
-            for (int w = 0; w < kKW; ++w) nx[w] = __ldg(p0 + 4 * w) & __ldg(p1 + 4 * w);
-            for (uint32_t st = 0; st < nst; ++st, ++it) {
-                uint32_t x[kKW];
-#pragma unroll
-                for (int w = 0; w < kKW; ++w) x[w] = nx[w];
-                if (st + 1 < nst) {
-#pragma unroll
-                    for (int w = 0; w < kKW; ++w) {
-                        const size_t o = ((size_t)(st + 1) * kKW + w) * 4;
-                        nx[w] = __ldg(p0 + o) & __ldg(p1 + o);
-                    }
-                }
-                const uint32_t s = it % kGStages;
-                mbar_wait_short(&sh.empty[s], ((it / kGStages) & 1u) ^ 1u);      // the MMAs that read this slot are done
-                const uint32_t base = stage0 + s * kStageBytes + dst0;
-#pragma unroll
-                for (int w = 0; w < kKW; ++w) {
-                    uint32_t o[8];
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) o[v] = (x[w] >> v) & 0x01010101u;   // byte j of o[v] = column 8 j + v of the word
-                    const uint32_t a0 = base + (uint32_t)w * nrows * 32u;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a0 + nrows * 16u), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
-                }
-                fence_proxy_async_smem();                    // my stores are visible to the tensor core's reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.full[s]);
-            }
+            if (is_a) produce_tile<128u>(p0, p1, nst, stages + dst0, sh.full, sh.empty, it, lane);
+            else produce_tile<256u>(p0, p1, nst, stages + dst0, sh.full, sh.empty, it, lane);
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------ MMA issuer ------------------------------
@@ -315,20 +323,16 @@ pair_gemm_kernel(PairGemmArgs args, int group)
 // ------------------------------------------------------------------------------------------
 // scores from finished count tensors (global memory), the quartets named by a range of planner entries
 // ------------------------------------------------------------------------------------------
-__global__ void __maxnreg__(128)
+__global__ void __launch_bounds__(kScoreWarps * 32, 1)
 score_counts_kernel(const uint32_t *__restrict__ counts, const uint4 *__restrict__ quartets, const uint2 *__restrict__ entries,
-                    const uint32_t *__restrict__ tile_list, const uint32_t *__restrict__ tile_range,
-                    const uint32_t *__restrict__ cell_off, const uint32_t *__restrict__ cell_count, int group, uint64_t seed,
+                    const uint32_t *__restrict__ nentries, uint64_t seed,
                     double *__restrict__ rscor, uint2 *__restrict__ rstat, uint32_t *__restrict__ minrank_out)
 {
     extern __shared__ __align__(1024) unsigned char pg_smem[];
     SvdScratch4 *scratch = reinterpret_cast<SvdScratch4 *>(pg_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SvdScratch4 &sv = scratch[warp];
-    const uint32_t tlo = tile_range[group], thi = tile_range[group + 1];
-    if (tlo >= thi) return;
-    const uint32_t last = __ldg(tile_list + thi - 1);
-    const uint32_t e_lo = __ldg(cell_off + __ldg(tile_list + tlo)), e_hi = __ldg(cell_off + last) + __ldg(cell_count + last);
+    const uint32_t e_lo = 0u, e_hi = nentries[0];          // entries = the quartets with valid tips, in tile order
     const uint32_t nwarps = gridDim.x * kScoreWarps;
     for (uint32_t base = e_lo + 4u * (blockIdx.x * kScoreWarps + warp); base < e_hi; base += 4u * nwarps) {
         const int nq = (int)min(4u, e_hi - base);
@@ -379,21 +383,6 @@ bool pairgemm_applies(int64_t ntips, int64_t m, int num_sms)
 }
 
 namespace {
-struct SideStream {             // one per device: the stream the scores run on beside the GEMM, and its events
-    std::mutex mu;
-    cudaStream_t stream[64] = {};
-    cudaError_t get(int dev, cudaStream_t *out)
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (!stream[dev & 63]) {
-            cudaError_t e = cudaStreamCreateWithFlags(&stream[dev & 63], cudaStreamNonBlocking);
-            if (e != cudaSuccess) return e;
-        }
-        *out = stream[dev & 63];
-        return cudaSuccess;
-    }
-};
-SideStream g_side;
 std::mutex g_attr_mu;
 uint64_t g_attr_done = 0;
 }  // namespace
@@ -419,10 +408,6 @@ cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_plane
             g_attr_done |= bit;
         }
     }
-    cudaStream_t side = nullptr;
-    cudaError_t e0 = g_side.get(dev, &side);
-    if (e0 != cudaSuccess) return e0;
-
     const uint32_t n = (uint32_t)ntips, np = n * (n - 1) / 2;
     const uint32_t ntr = (np + kRP - 1) / kRP, ntc = (np + kCP - 1) / kCP, ncells = ntr * ntc;
     // Quartet chunks: 1 KB of counts per quartet lives in scratch unless the caller wants the counts anyway.
@@ -446,7 +431,7 @@ cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_plane
         uint32_t *cell_count = (uint32_t *)(scratch + o_count), *cell_off = (uint32_t *)(scratch + o_off);
         uint32_t *flag = (uint32_t *)(scratch + o_flag), *fscan = (uint32_t *)(scratch + o_fscan);
         uint32_t *cell_fill = (uint32_t *)(scratch + o_fill), *tile_list = (uint32_t *)(scratch + o_list);
-        uint32_t *tile_range = (uint32_t *)(scratch + o_range);
+        uint32_t *ntiles = (uint32_t *)(scratch + o_range);
         uint2 *entries = (uint2 *)(scratch + o_entries);
         uint32_t *counts = d_counts ? d_counts + (size_t)c0 * 256 : (uint32_t *)(scratch + o_counts);
 
@@ -456,30 +441,21 @@ cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_plane
         PG_CHECK(cub::DeviceScan::ExclusiveSum(scratch + o_temp, temp_bytes, cell_count, cell_off, (int)ncells + 1, stream));
         pg_flag_kernel<<<cbk, 256, 0, stream>>>(cell_count, ncells, flag);
         PG_CHECK(cub::DeviceScan::ExclusiveSum(scratch + o_temp, temp_bytes, flag, fscan, (int)ncells + 1, stream));
-        pg_compact_kernel<<<cbk, 256, 0, stream>>>(cell_count, fscan, ncells, (uint32_t)num_sms, tile_list, tile_range);
+        pg_compact_kernel<<<cbk, 256, 0, stream>>>(cell_count, fscan, ncells, tile_list, ntiles);
         pg_fill_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_off, cell_fill, entries);
         g_launches += 7;
         PG_CHECK(cudaGetLastError());
 
         PairGemmArgs args;
         args.planes = d_planes; args.row_u4 = plan.row_u4; args.ntips = n; args.npairs = np; args.ntc = ntc;
-        args.tile_list = tile_list; args.tile_range = tile_range; args.cell_off = cell_off; args.cell_count = cell_count;
+        args.tile_list = tile_list; args.ntiles = ntiles; args.cell_off = cell_off; args.cell_count = cell_count;
         args.entries = entries; args.counts = counts;
-        // group g: GEMM on the caller's stream, its scores on the side stream behind an event -- beside the GEMM of g + 1
-        cudaEvent_t ev[kGroups + 1];
-        for (int g = 0; g <= kGroups; ++g) PG_CHECK(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
-        for (int g = 0; g < kGroups; ++g) {
-            pair_gemm_kernel<<<num_sms, kGemmThreads, gemm_smem, stream>>>(args, g);
-            PG_CHECK(cudaEventRecord(ev[g], stream));
-            PG_CHECK(cudaStreamWaitEvent(side, ev[g], 0));
-            score_counts_kernel<<<num_sms, kScoreWarps * 32, score_smem, side>>>(counts, quartets + c0, entries, tile_list, tile_range,
-                                                                                 cell_off, cell_count, g, seed, d_rscor + 3 * c0,
-                                                                                 rstat + c0, d_minrank ? d_minrank + c0 : nullptr);
-            g_launches += 2;
-        }
-        PG_CHECK(cudaEventRecord(ev[kGroups], side));
-        PG_CHECK(cudaStreamWaitEvent(stream, ev[kGroups], 0));            // the caller's stream owns the results again
-        for (int g = 0; g <= kGroups; ++g) cudaEventDestroy(ev[g]);
+        pair_gemm_kernel<<<num_sms, kGemmThreads, gemm_smem, stream>>>(args);
+        // cell_off[ncells] = number of bucketed quartets (the scan runs over ncells + 1 elements)
+        score_counts_kernel<<<num_sms, kScoreWarps * 32, score_smem, stream>>>(counts, quartets + c0, entries, cell_off + ncells, seed,
+                                                                             d_rscor + 3 * c0, rstat + c0,
+                                                                             d_minrank ? d_minrank + c0 : nullptr);
+        g_launches += 2;
         PG_CHECK(cudaGetLastError());
         cudaFreeAsync(scratch, stream);
     }

@@ -62,28 +62,30 @@ def upload(array: np.ndarray, device):
     return t
 
 
-_PINNED_POOL: list = []
+_PINNED_POOL: list = []          # [pinned uint8 tensor, weak reference to the ndarray handed out from it]
 
 
 def _pinned_array(shape, dtype):
     """Result array backed by page-locked memory (device -> host copies into it are asynchronous DMA, not staged
-    through a driver buffer).  The backing tensors are pooled: one is reused once the arrays handed out from it have been
-    dropped by the caller (the ndarray keeps its tensor alive, so the tensor's reference count tells)."""
-    import sys
+    through a driver buffer).  The backing tensors are pooled: one is reused once every array handed out from it has
+    been dropped by the caller (all views keep the tensor's base ndarray alive; a weak reference to it tells)."""
+    import weakref
     import torch
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
-    chosen = None
-    for t in _PINNED_POOL:
-        if nbytes <= t.numel() <= 2 * nbytes + 4096 and sys.getrefcount(t) <= 3:      # pool, loop variable, argument
-            chosen = t
+    entry = None
+    for cand in _PINNED_POOL:
+        if nbytes <= cand[0].numel() <= 2 * nbytes + 4096 and cand[1]() is None:
+            entry = cand
             break
-    if chosen is None:
-        chosen = torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True)
-        _PINNED_POOL.append(chosen)
+    if entry is None:
+        entry = [torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True), None]
+        _PINNED_POOL.append(entry)
         if len(_PINNED_POOL) > 16:
             _PINNED_POOL.pop(0)
-    return chosen.numpy()[:nbytes].view(dtype).reshape(shape)
+    base = entry[0].numpy()
+    entry[1] = weakref.ref(base)
+    return base[:nbytes].view(dtype).reshape(shape)
 
 
 def _as_locus(tmpmap: np.ndarray):
