@@ -143,8 +143,8 @@ int tq_boot_pack_rows(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntip
  *   d_counts u32[m][256] or NULL = mats[0] row-major (index 64a+16b+4c+d),
  *   d_minrank u32[m] or NULL.
  * subsample != 0 -> one SNP per locus (subsample_chunk_to_matrices); 0 -> all SNPs
- * (full_chunk_to_matrices; a list that holds >= 30 % of all C(ntips,4) quartets goes through one u8 GEMM over tip
- * pairs on tcgen05.mma, which needs the tips of a quartet in ascending order, as the reference produces them).  Tip indices must be < ntips (checked on the device: offending
+ * (full_chunk_to_matrices; chunks of the list whose quartets fill the tiles of a tip-pair grid densely -- exhaustive
+ * lists and contiguous ranges of them -- go through one u8 GEMM over tip pairs on tcgen05.mma, decided on the device).  Tip indices must be < ntips (checked on the device: offending
  * quartets get best = 0xFFFFFFFF and the call's status word, if given, is set non-zero).
  */
 int tq_resolve(const tq_plan *plan, const uint32_t *d_planes, int64_t ntips,
@@ -214,6 +214,11 @@ int64_t tq_launch_count(void);
 /* name of the resolve kernel variant the last tq_resolve / tq_resolve_host launched
  * ("tq::resolve_mma_kernel<true>", ...); a static string, never NULL */
 const char *tq_last_kernel(void);
+
+/* Full mode routes every chunk (2^18 quartets) of a list on the device: to the tip-pair GEMM when its tiles are dense
+ * (>= 30 quartets per 128-quartet tile, all tips ascending), to the per-quartet kernel otherwise.  out[0] / out[1] =
+ * chunks routed to the GEMM / to the per-quartet kernel since the library was loaded (read after synchronising). */
+int tq_pairgemm_stats(int64_t out[2]);
 
 /* Tuning / test hooks; process-wide, initialised from the environment (TQ_KERNEL, TQ_MMA_FLUSH).
  *   "kernel"           0 = chosen by launch size and mode (default), 1 = one-warp-per-quartet POPC kernel,

@@ -6,6 +6,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module")
+def tb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import tetrad_b200
+    return tetrad_b200
+
+
 @pytest.mark.parametrize("shape,seed", [((9, 700, 2600), 1), ((6, 1500, 4000), 2), ((5, 3, 9), 3)])
 def test_device_bootstrap_equals_oracle_sampler(oracle, shape, seed):
     import tetrad_b200
@@ -56,3 +64,54 @@ def test_replicate_loop_uses_device_bootstrap(oracle, tmp_path):
     _, ostat, oscor = oracle.new_infer_resolved_quartets(tmparr, tmpmap, q.astype(np.uint32), True)
     assert (nsnps == ostat[:, 1]).all() and (best == ostat[:, 0]).all()
     np.testing.assert_allclose(scores, oscor, rtol=1e-5, atol=1e-6)
+
+
+def test_tip_row_ranges_pack_the_same_planes(tb):
+    """tq_pack_rows / tq_boot_pack_rows over any split of the tip rows write exactly the planes of the unsharded call
+    (the ambiguity coins are keyed by the global tip index): what lets every rank of a multi-GPU run pack only its share
+    before the all-gather."""
+    import torch
+    from tetrad_b200 import synth
+    d = synth.generate(11, 900, 3600, seed=31, p_ambig=0.05)
+    db = synth.prepare_database(d.snps, d.snpsmap, seed=4)
+    rng = np.random.default_rng(5)
+    lidxs = rng.choice(len(db["spans"]), len(db["spans"]), replace=True)
+    whole = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+    ref0 = whole.planes.clone()
+    whole.load_bootstrap(db["seqarr"], db["spans"], lidxs, 123, 456)
+    ref1 = whole.planes.clone()
+    part = tb.QuartetResolver(device=0)
+    for cuts in ((0, 4, 11), (0, 1, 2, 9, 11)):
+        part.load(db["tmparr"], db["tmpmap"], tip_range=(0, 0))
+        part.planes.zero_()
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            part.pack((lo, hi))
+        assert torch.equal(part.planes, ref0)
+        for i, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
+            if i == 0:
+                part.load_bootstrap(db["seqarr"], db["spans"], lidxs, 123, 456, tip_range=(lo, hi))
+                rows = {(lo, hi): part.planes[lo:hi].clone()}
+            else:
+                part.load_bootstrap(db["seqarr"], db["spans"], lidxs, 123, 456, tip_range=(lo, hi))
+                rows[(lo, hi)] = part.planes[lo:hi].clone()
+        for (lo, hi), got in rows.items():
+            assert torch.equal(got, ref1[lo:hi])
+    whole.close(); part.close()
+
+
+def test_device_sampler_equals_its_oracle_and_is_distinct(tb):
+    """tq_sample_quartets: quartet i = unrank(pi_key(i)); bit-exact against the numpy restatement of the permutation,
+    distinct, ascending tips, any index range on its own."""
+    from math import comb
+    from oracle import sample_oracle
+    from tetrad_b200 import combinations as cb
+    for n, key, count in ((12, 3, 495), (200, 0x1234567890ABCDEF, 60000), (500, 99, 20000)):
+        got = cb.device_sample(n, key, count).cpu().numpy().view(np.uint32)
+        want = cb.unrank_quartets(sample_oracle.permute(np.arange(count), n, key), n)
+        assert (got == want).all()
+        assert len(np.unique(got, axis=0)) == count and (np.diff(got.astype(np.int64), axis=1) > 0).all() and got.max() < n
+        part = cb.device_sample(n, key, 1000 if count > 1000 else count // 2, start=count // 3).cpu().numpy().view(np.uint32)
+        assert (part == want[count // 3: count // 3 + len(part)]).all()
+    from tetrad_b200._lib import TetradB200Error
+    with pytest.raises(TetradB200Error):
+        cb.device_sample(12, 1, 10, start=comb(12, 4) - 5)

@@ -417,3 +417,50 @@ def test_pairgemm_full_mode_small_and_ragged(tb, oracle):
         assert (bstat.cpu().numpy().view(np.uint32)[keep] == ostat[:nb][keep]).all()
         assert bstat.cpu().numpy().view(np.uint32)[nb // 2, 0] == 0xFFFFFFFF
         eng.close()
+
+
+def test_full_mode_is_routed_on_the_device(tb, oracle):
+    """Full mode, default kernel rule: an exhaustive list (and a contiguous eighth of it, one rank's share of an 8-GPU
+    run) goes to the tip-pair GEMM, a sparse random sample and a list with a quartet whose tips are not ascending go to
+    the per-quartet kernel; the decision is taken by the planner on the device and every route gives the same bits."""
+    import torch
+    from itertools import combinations
+    from tetrad_b200 import _lib, synth
+    n = 40
+    d = synth.generate(n, 800, 3000, seed=77)
+    db = synth.prepare_database(d.snps, d.snpsmap, seed=7)
+    allq = np.array(list(combinations(range(n), 4)), dtype=np.uint32)           # 91 390 quartets
+    eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+
+    def routed(q):
+        torch.cuda.synchronize()
+        before = _lib.pairgemm_stats()
+        out = eng.resolve(q, False, want_counts=True)
+        torch.cuda.synchronize()
+        after = _lib.pairgemm_stats()
+        return (after[0] - before[0], after[1] - before[1]), out
+
+    route, full = routed(allq)
+    assert route == (1, 0), route
+    share = allq[len(allq) // 8 * 3: len(allq) // 8 * 4]
+    route, part = routed(share)
+    assert route == (1, 0), route
+    lo = len(allq) // 8 * 3
+    for a, b in zip(part, full):
+        assert torch.equal(a, b[lo: lo + len(share)])
+    pick = np.sort(np.random.default_rng(3).choice(len(allq), 4000, replace=False))
+    route, sparse = routed(allq[pick])
+    assert route == (0, 1), route
+    idx = torch.from_numpy(pick).to(full[0].device)
+    for a, b in zip(sparse, full):
+        assert torch.equal(a, b[idx])
+    mixed = allq.copy()
+    mixed[5] = mixed[5][[1, 0, 2, 3]]                                            # valid tips, not ascending
+    route, res = routed(mixed)
+    assert route == (0, 1), route
+    eng.check_status()
+    keep = np.arange(len(allq)) != 5
+    assert torch.equal(res[0][torch.from_numpy(keep).to(res[0].device)], full[0][torch.from_numpy(keep).to(res[0].device)])
+    _, ostat, oscor, det = oracle.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], allq[::97], False, return_details=True)
+    assert (full[2].cpu().numpy().view(np.uint32).reshape(-1, 16, 16)[::97] == det["mats"][:, 0]).all()
+    eng.close()

@@ -131,6 +131,13 @@ const char *tq_last_error(void) { return g_err; }
 int64_t tq_launch_count(void) { return tq::g_launches.load(); }
 const char *tq_last_kernel(void) { return tq::g_last_kernel.load(); }
 
+int tq_pairgemm_stats(int64_t out[2])
+{
+    if (!out) return fail(TQ_EINVAL, "tq_pairgemm_stats: out is NULL");
+    tq::pairgemm_stats(out);
+    return TQ_OK;
+}
+
 int tq_set_option(const char *name, int64_t value)
 {
     if (!name) return fail(TQ_EINVAL, "tq_set_option: null name");

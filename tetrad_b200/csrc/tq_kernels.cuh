@@ -38,11 +38,18 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
                            uint32_t *d_minrank, uint32_t *d_status, int num_sms,
                            cudaStream_t stream);
 
-// full mode over tip pairs on tcgen05 (tq_pairgemm.cu): whether a launch of m quartets of ntips tips is dense enough for it
+// full mode over tip pairs on tcgen05 (tq_pairgemm.cu): whether a launch is worth planning; the planner then routes every
+// chunk of the list, on the device, to the GEMM (dense) or to the per-quartet kernel (launch_resolve_mma_full with the
+// route flag as `d_skip`); force = 5 always takes the GEMM
 bool pairgemm_applies(int64_t ntips, int64_t m, int num_sms);
 cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips, const uint32_t *d_quartets,
                                     int64_t m, uint64_t seed, double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
-                                    uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream);
+                                    uint32_t *d_minrank, uint32_t *d_status, int num_sms, int force, cudaStream_t stream);
+cudaError_t launch_resolve_mma_full(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips, const uint32_t *d_quartets,
+                                    int64_t m, uint64_t seed, double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
+                                    uint32_t *d_minrank, uint32_t *d_status, int num_sms, const uint32_t *d_skip,
+                                    cudaStream_t stream);
+void pairgemm_stats(int64_t out[2]);     // chunks routed to the GEMM / to the per-quartet kernel since load
 
 cudaError_t launch_unrank(const int64_t *d_ranks, int64_t start, int64_t m, uint32_t ntips, uint32_t *d_quartets,
                           cudaStream_t stream);

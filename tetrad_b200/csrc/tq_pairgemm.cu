@@ -14,8 +14,11 @@
 // they are unpacked once per PAIR and tile:
 //
 //   tile        8 row pairs (t0 < t1) x 16 column pairs (t2 < t3) = 128 x 256 outputs = 128 candidate quartets;
-//               pairs are numbered by (t1, t0) and by (t2, t3), so the tiles that hold wanted quartets (t1 < t2) form a
-//               staircase -- a device planner buckets the quartet list by tile, and only non-empty tiles are computed
+//               pairs are numbered lexicographically, so the tiles that hold wanted quartets (t1 < t2) form a staircase
+//               -- a device planner buckets the quartet list by tile, only non-empty tiles are computed, and the planner
+//               also DECIDES, on the device, whether the chunk is dense enough for the GEMM (>= 30 quartets per tile)
+//               or goes to the per-quartet kernel: no host synchronisation, and a rank's contiguous share of an
+//               exhaustive list stays on the GEMM however many ranks there are
 //   K           all 32-column words of the packed rows; one tcgen05.mma (M = 128, N = 256, K = 32 bytes) per word
 //   producers   12 warps, thread = one operand row (pair, ab): two 4-byte plane loads, one AND, and the 32 columns of
 //               the word become 32 bytes {0, 1} -- (x >> v) & 0x01010101 for v = 0..7 -- written as two 16-byte K chunks
@@ -81,28 +84,23 @@ struct PairGemmArgs {
     const uint32_t *cell_count;
     const uint2 *entries;          // (quartet index, local row pair << 8 | local column pair), bucketed by cell
     uint32_t *counts;              // [m][256]
+    const uint32_t *flags;         // flags[0] != 0: this chunk takes the GEMM route (else the kernels return at once)
 };
 
-// pair numbering: row pairs by (t1, t0): rp = t1 (t1 - 1) / 2 + t0;  column pairs by (t2, t3): cp = off(t2) + t3 - t2 - 1
-__host__ __device__ __forceinline__ uint32_t rowpair_index(uint32_t t0, uint32_t t1) { return t1 * (t1 - 1) / 2 + t0; }
-__host__ __device__ __forceinline__ uint32_t colpair_offset(uint32_t t2, uint32_t n) { return t2 * (2 * n - 1 - t2) / 2; }
-__host__ __device__ __forceinline__ uint32_t colpair_index(uint32_t t2, uint32_t t3, uint32_t n) { return colpair_offset(t2, n) + t3 - t2 - 1; }
+// Pair numbering, rows and columns alike: pairs (u < v) in lexicographic order, index = off(u) + v - u - 1.  A contiguous
+// range of a lexicographic quartet list (one rank's share, one chunk) is then a contiguous range of row pairs: its tiles
+// stay dense.
+__host__ __device__ __forceinline__ uint32_t pair_offset(uint32_t u, uint32_t n) { return u * (2 * n - 1 - u) / 2; }
+__host__ __device__ __forceinline__ uint32_t pair_index(uint32_t u, uint32_t v, uint32_t n) { return pair_offset(u, n) + v - u - 1; }
 
-__device__ __forceinline__ uint2 unrank_rowpair(uint32_t rp)
+__device__ __forceinline__ uint2 unrank_pair(uint32_t idx, uint32_t n)
 {
-    uint32_t t1 = (uint32_t)((1.0 + sqrt(1.0 + 8.0 * (double)rp)) * 0.5);
-    while (t1 * (t1 - 1) / 2 > rp) --t1;
-    while (t1 * (t1 + 1) / 2 <= rp) ++t1;
-    return make_uint2(rp - t1 * (t1 - 1) / 2, t1);
-}
-__device__ __forceinline__ uint2 unrank_colpair(uint32_t cp, uint32_t n)
-{
-    uint32_t lo = 0, hi = n - 2;                     // largest t2 with off(t2) <= cp
+    uint32_t lo = 0, hi = n - 2;                     // largest u with off(u) <= idx
     while (lo < hi) {
         const uint32_t mid = (lo + hi + 1) >> 1;
-        if (colpair_offset(mid, n) <= cp) lo = mid; else hi = mid - 1;
+        if (pair_offset(mid, n) <= idx) lo = mid; else hi = mid - 1;
     }
-    return make_uint2(lo, lo + 1 + (cp - colpair_offset(lo, n)));
+    return make_uint2(lo, lo + 1 + (idx - pair_offset(lo, n)));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -110,24 +108,51 @@ __device__ __forceinline__ uint2 unrank_colpair(uint32_t cp, uint32_t n)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool quartet_cell(uint4 t, uint32_t n, uint32_t ntc, uint32_t &cell, uint32_t &local)
 {
-    if (!(t.x < t.y && t.y < t.z && t.z < t.w && t.w < n)) return false;
-    const uint32_t rp = rowpair_index(t.x, t.y), cp = colpair_index(t.z, t.w, n);
+    if (!(t.x < t.y && t.y < t.z && t.z < t.w && t.w < n)) return false;      // out of range, or not ascending
+    const uint32_t rp = pair_index(t.x, t.y, n), cp = pair_index(t.z, t.w, n);
     cell = (rp / kRP) * ntc + cp / kCP;
     local = ((rp % kRP) << 8) | (cp % kCP);
     return true;
 }
 
-// quartets whose tips are out of range (or not ascending) never reach a tile: they get the error marks here
+// stats[0]: quartets with a tip out of range; stats[1]: quartets in range whose tips are not ascending (the GEMM needs
+// ascending tips; a chunk that holds one goes to the per-quartet kernel, which does not care)
 __global__ void __launch_bounds__(256) pg_count_kernel(const uint4 *__restrict__ quartets, int64_t m, uint32_t n, uint32_t ntc,
-                                                       uint32_t *__restrict__ cell_count, double *__restrict__ rscor,
-                                                       uint2 *__restrict__ rstat, uint32_t *__restrict__ status)
+                                                       uint32_t *__restrict__ cell_count, uint32_t *__restrict__ stats)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= m) return;
+    const uint4 t = __ldg(quartets + q);
     uint32_t cell, local;
-    if (quartet_cell(__ldg(quartets + q), n, ntc, cell, local)) {
-        atomicAdd(cell_count + cell, 1u);
-    } else {
+    if (quartet_cell(t, n, ntc, cell, local)) atomicAdd(cell_count + cell, 1u);
+    else if (t.x >= n || t.y >= n || t.z >= n || t.w >= n) atomicAdd(stats, 1u);
+    else atomicAdd(stats + 1, 1u);
+}
+
+// The chunk's route, decided where the planner's result lives.  flags[0] = 1: tip-pair GEMM + score kernel; 0: the
+// per-quartet tensor-core kernel (which then skips nothing).  Every tile costs the same and about as much as 30 quartets
+// of the per-quartet kernel (C2: 4.95 us per tile against 0.198 - 0.030 us per quartet; both scale with the columns).
+// g_route counts the decisions (host-mapped: tq_pairgemm_stats).
+__global__ void pg_decide_kernel(const uint32_t *__restrict__ ntiles, const uint32_t *__restrict__ nentries,
+                                 const uint32_t *__restrict__ stats, int force, uint32_t *__restrict__ flags,
+                                 unsigned long long *__restrict__ route)
+{
+    const bool dense = (uint64_t)ntiles[0] * 30ull <= (uint64_t)nentries[0];
+    const bool gemm = stats[1] == 0u && nentries[0] > 0u && (force == 5 || dense);
+    flags[0] = gemm ? 1u : 0u;
+    atomicAdd(route + (gemm ? 0 : 1), 1ull);
+}
+
+// GEMM route only: quartets with a tip out of range never reach a tile; they get the error marks here
+__global__ void __launch_bounds__(256) pg_mark_bad_kernel(const uint4 *__restrict__ quartets, int64_t m, uint32_t n,
+                                                          const uint32_t *__restrict__ flags, double *__restrict__ rscor,
+                                                          uint2 *__restrict__ rstat, uint32_t *__restrict__ status)
+{
+    if (!flags[0]) return;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const uint4 t = __ldg(quartets + q);
+    if (t.x >= n || t.y >= n || t.z >= n || t.w >= n) {
         rstat[q] = make_uint2(0xFFFFFFFFu, 0u);
         rscor[3 * q] = rscor[3 * q + 1] = rscor[3 * q + 2] = 0.0;
         if (status) atomicOr(status, 1u);
@@ -217,6 +242,7 @@ __device__ __forceinline__ void produce_tile(const uint32_t *__restrict__ p0, co
 __global__ void __launch_bounds__(kGemmThreads, 1)
 pair_gemm_kernel(PairGemmArgs args)
 {
+    if (!args.flags[0]) return;                           // the planner sent this chunk to the per-quartet kernel
     extern __shared__ __align__(1024) unsigned char pg_smem[];
     unsigned char *stages = pg_smem;
     PairGemmShared &sh = *reinterpret_cast<PairGemmShared *>(pg_smem + kGStages * kStageBytes);
@@ -248,8 +274,8 @@ pair_gemm_kernel(PairGemmArgs args)
             const uint32_t cell = __ldg(args.tile_list + tile);
             const uint32_t tr = cell / args.ntc, tc = cell % args.ntc;
             uint2 pr;                                        // my pair: (tip of the first plane, tip of the second plane)
-            if (is_a) { const uint32_t rp = tr * kRP + (r >> 4); pr = unrank_rowpair(rp < args.npairs ? rp : args.npairs - 1); }
-            else { const uint32_t cp = tc * kCP + (r >> 4); pr = unrank_colpair(cp < args.npairs ? cp : args.npairs - 1, args.ntips); }
+            if (is_a) { const uint32_t rp = tr * kRP + (r >> 4); pr = unrank_pair(rp < args.npairs ? rp : args.npairs - 1, args.ntips); }
+            else { const uint32_t cp = tc * kCP + (r >> 4); pr = unrank_pair(cp < args.npairs ? cp : args.npairs - 1, args.ntips); }
             const uint32_t *p0 = args.planes + (size_t)pr.x * args.row_u4 * 4 + ((r >> 2) & 3u);
             const uint32_t *p1 = args.planes + (size_t)pr.y * args.row_u4 * 4 + (r & 3u);
             if (is_a) produce_tile<128u>(p0, p1, nst, stages + dst0, sh.full, sh.empty, it, lane);
@@ -325,9 +351,10 @@ pair_gemm_kernel(PairGemmArgs args)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScoreWarps * 32, 1)
 score_counts_kernel(const uint32_t *__restrict__ counts, const uint4 *__restrict__ quartets, const uint2 *__restrict__ entries,
-                    const uint32_t *__restrict__ nentries, uint64_t seed,
+                    const uint32_t *__restrict__ nentries, const uint32_t *__restrict__ flags, uint64_t seed,
                     double *__restrict__ rscor, uint2 *__restrict__ rstat, uint32_t *__restrict__ minrank_out)
 {
+    if (!flags[0]) return;
     extern __shared__ __align__(1024) unsigned char pg_smem[];
     SvdScratch4 *scratch = reinterpret_cast<SvdScratch4 *>(pg_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -373,25 +400,49 @@ score_counts_kernel(const uint32_t *__restrict__ counts, const uint4 *__restrict
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// Whether a full-mode launch is worth planning at all (the decision proper is taken per chunk on the device): enough
+// quartets for a persistent kernel, a pair x pair tile grid that fits a few million cells.
 bool pairgemm_applies(int64_t ntips, int64_t m, int num_sms)
 {
     if (ntips < 5 || ntips > 2048 || m < (int64_t)num_sms * 16) return false;
-    const double n = (double)ntips, total = n * (n - 1) * (n - 2) * (n - 3) / 24.0;
     const uint64_t np = (uint64_t)ntips * (ntips - 1) / 2;
     const uint64_t ncells = ((np + kRP - 1) / kRP) * ((np + kCP - 1) / kCP);
-    return (double)m >= 0.30 * total && ncells <= (4u << 20);
+    return ncells <= (4u << 20);
 }
 
 namespace {
 std::mutex g_attr_mu;
 uint64_t g_attr_done = 0;
+// chunks routed to the GEMM / to the per-quartet kernel since load: host-mapped pinned memory the decide kernel bumps
+unsigned long long *g_route_host = nullptr;
+std::mutex g_route_mu;
+unsigned long long *route_counters()
+{
+    std::lock_guard<std::mutex> lk(g_route_mu);
+    if (!g_route_host) {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&g_route_host), 2 * sizeof(unsigned long long),
+                          cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        g_route_host[0] = g_route_host[1] = 0ull;
+    }
+    return g_route_host;
+}
 }  // namespace
 
-#define PG_CHECK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { if (scratch) cudaFreeAsync(scratch, stream); return e__; } } while (0)
+void pairgemm_stats(int64_t out[2])
+{
+    unsigned long long *r = route_counters();
+    out[0] = r ? (int64_t)r[0] : 0;
+    out[1] = r ? (int64_t)r[1] : 0;
+}
+
+#define PG_CHECK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cudaFreeAsync(scratch, stream); return e__; } } while (0)
 
 cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips, const uint32_t *d_quartets,
                                     int64_t m, uint64_t seed, double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
-                                    uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream)
+                                    uint32_t *d_minrank, uint32_t *d_status, int num_sms, int force, cudaStream_t stream)
 {
     if (m == 0) return cudaSuccess;
     int dev = 0;
@@ -408,58 +459,70 @@ cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_plane
             g_attr_done |= bit;
         }
     }
+    unsigned long long *route_host = route_counters(), *route_dev = nullptr;
+    if (!route_host || cudaHostGetDevicePointer(reinterpret_cast<void **>(&route_dev), route_host, 0) != cudaSuccess)
+        return cudaErrorMemoryAllocation;
+
     const uint32_t n = (uint32_t)ntips, np = n * (n - 1) / 2;
     const uint32_t ntr = (np + kRP - 1) / kRP, ntc = (np + kCP - 1) / kCP, ncells = ntr * ntc;
-    // Quartet chunks: 1 KB of counts per quartet lives in scratch unless the caller wants the counts anyway.
-    const int64_t chunk_cap = d_counts ? m : (int64_t)1 << 21;
+    // Chunks of the list: 1 KB of counts per quartet lives in scratch (unless the caller wants the counts anyway), and
+    // every chunk is routed on its own.
+    const int64_t chunk_cap = (int64_t)1 << 18;
     const uint4 *quartets = reinterpret_cast<const uint4 *>(d_quartets);
     uint2 *rstat = reinterpret_cast<uint2 *>(d_rstat);
+    size_t temp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)ncells + 1, stream);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const int64_t mcap = m < chunk_cap ? m : chunk_cap;
+    // scratch: cell_count | cell_off (+1) | flag | flag_scan (+1) | cell_fill | tile_list | small words | entries | counts | cub temp
+    const size_t cb = up(((size_t)ncells + 1) * 4);
+    const size_t o_count = 0, o_off = o_count + cb, o_flag = o_off + cb, o_fscan = o_flag + cb, o_fill = o_fscan + cb,
+                 o_list = o_fill + cb, o_small = o_list + cb, o_entries = o_small + 256, o_counts = o_entries + up((size_t)mcap * 8),
+                 o_temp = o_counts + (d_counts ? 0 : up((size_t)mcap * 1024)), total = o_temp + up(temp_bytes);
+    char *scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, total, stream);
+    if (e != cudaSuccess) return e;
+    uint32_t *cell_count = (uint32_t *)(scratch + o_count), *cell_off = (uint32_t *)(scratch + o_off);
+    uint32_t *flag = (uint32_t *)(scratch + o_flag), *fscan = (uint32_t *)(scratch + o_fscan);
+    uint32_t *cell_fill = (uint32_t *)(scratch + o_fill), *tile_list = (uint32_t *)(scratch + o_list);
+    uint32_t *small = (uint32_t *)(scratch + o_small);          // [0] tiles, [1..2] stats, [4] route flag
+    uint32_t *ntiles = small, *stats = small + 1, *flags = small + 4;
+    uint2 *entries = (uint2 *)(scratch + o_entries);
 
     for (int64_t c0 = 0; c0 < m; c0 += chunk_cap) {
         const int64_t mc = (m - c0 < chunk_cap) ? m - c0 : chunk_cap;
-        // scratch: cell_count | cell_off (+1) | flag | flag_scan (+1) | cell_fill | tile_list | tile_range | entries | counts | cub temp
-        size_t temp_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)ncells + 1, stream);
-        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-        const size_t cb = up(((size_t)ncells + 1) * 4);
-        const size_t o_count = 0, o_off = o_count + cb, o_flag = o_off + cb, o_fscan = o_flag + cb, o_fill = o_fscan + cb,
-                     o_list = o_fill + cb, o_range = o_list + cb, o_entries = o_range + 256, o_counts = o_entries + up((size_t)mc * 8),
-                     o_temp = o_counts + (d_counts ? 0 : up((size_t)mc * 1024)), total = o_temp + up(temp_bytes);
-        char *scratch = nullptr;
-        cudaError_t e = cudaMallocAsync(&scratch, total, stream);
-        if (e != cudaSuccess) return e;
-        uint32_t *cell_count = (uint32_t *)(scratch + o_count), *cell_off = (uint32_t *)(scratch + o_off);
-        uint32_t *flag = (uint32_t *)(scratch + o_flag), *fscan = (uint32_t *)(scratch + o_fscan);
-        uint32_t *cell_fill = (uint32_t *)(scratch + o_fill), *tile_list = (uint32_t *)(scratch + o_list);
-        uint32_t *ntiles = (uint32_t *)(scratch + o_range);
-        uint2 *entries = (uint2 *)(scratch + o_entries);
         uint32_t *counts = d_counts ? d_counts + (size_t)c0 * 256 : (uint32_t *)(scratch + o_counts);
-
-        PG_CHECK(cudaMemsetAsync(scratch, 0, o_list, stream));            // counts, offsets, flags, scans, fills
+        PG_CHECK(cudaMemsetAsync(scratch, 0, o_entries, stream));         // counts, offsets, flags, scans, fills, small words
         const unsigned qb = (unsigned)((mc + 255) / 256), cbk = (ncells + 1 + 255) / 256;
-        pg_count_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_count, d_rscor + 3 * c0, rstat + c0, d_status);
+        pg_count_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_count, stats);
         PG_CHECK(cub::DeviceScan::ExclusiveSum(scratch + o_temp, temp_bytes, cell_count, cell_off, (int)ncells + 1, stream));
         pg_flag_kernel<<<cbk, 256, 0, stream>>>(cell_count, ncells, flag);
         PG_CHECK(cub::DeviceScan::ExclusiveSum(scratch + o_temp, temp_bytes, flag, fscan, (int)ncells + 1, stream));
         pg_compact_kernel<<<cbk, 256, 0, stream>>>(cell_count, fscan, ncells, tile_list, ntiles);
+        // cell_off[ncells] = number of bucketed quartets (the scan runs over ncells + 1 elements)
+        pg_decide_kernel<<<1, 1, 0, stream>>>(ntiles, cell_off + ncells, stats, force, flags, route_dev);
         pg_fill_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_off, cell_fill, entries);
-        g_launches += 7;
+        pg_mark_bad_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, flags, d_rscor + 3 * c0, rstat + c0, d_status);
+        g_launches += 9;
         PG_CHECK(cudaGetLastError());
 
         PairGemmArgs args;
         args.planes = d_planes; args.row_u4 = plan.row_u4; args.ntips = n; args.npairs = np; args.ntc = ntc;
         args.tile_list = tile_list; args.ntiles = ntiles; args.cell_off = cell_off; args.cell_count = cell_count;
-        args.entries = entries; args.counts = counts;
+        args.entries = entries; args.counts = counts; args.flags = flags;
         pair_gemm_kernel<<<num_sms, kGemmThreads, gemm_smem, stream>>>(args);
-        // cell_off[ncells] = number of bucketed quartets (the scan runs over ncells + 1 elements)
-        score_counts_kernel<<<num_sms, kScoreWarps * 32, score_smem, stream>>>(counts, quartets + c0, entries, cell_off + ncells, seed,
-                                                                             d_rscor + 3 * c0, rstat + c0,
+        score_counts_kernel<<<num_sms, kScoreWarps * 32, score_smem, stream>>>(counts, quartets + c0, entries, cell_off + ncells, flags,
+                                                                             seed, d_rscor + 3 * c0, rstat + c0,
                                                                              d_minrank ? d_minrank + c0 : nullptr);
         g_launches += 2;
         PG_CHECK(cudaGetLastError());
-        cudaFreeAsync(scratch, stream);
+        // the other route: the per-quartet kernel returns at once when flags[0] says the GEMM took the chunk
+        PG_CHECK(launch_resolve_mma_full(plan, d_planes, ntips, d_quartets + 4 * c0, mc, seed, d_rscor + 3 * c0, d_rstat + 2 * c0,
+                                         d_counts ? d_counts + (size_t)c0 * 256 : nullptr, d_minrank ? d_minrank + c0 : nullptr,
+                                         d_status, num_sms, flags, stream));
     }
-    g_last_kernel = "tq::pair_gemm_kernel (tcgen05.mma kind::i8) + tq::score_counts_kernel";
+    cudaFreeAsync(scratch, stream);
+    g_last_kernel = "tq::pair_gemm_kernel (tcgen05.mma kind::i8) + tq::score_counts_kernel | tq::resolve_mma_kernel<false>, routed per chunk on the device";
     return cudaSuccess;
 }
 

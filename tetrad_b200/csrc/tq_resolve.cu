@@ -596,8 +596,9 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
                    const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
                    double *__restrict__ rscor, uint2 *__restrict__ rstat,
                    uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
-                   uint32_t *__restrict__ status, uint32_t flush_every)
+                   uint32_t *__restrict__ status, uint32_t flush_every, const uint32_t *__restrict__ skip)
 {
+    if (skip && skip[0]) return;                     // full mode: the tip-pair GEMM took this chunk (tq_pairgemm.cu)
     using Shared = MmaShared<NC, NS>;
     constexpr int kSlots = Shared::kSlots;
     static_assert(kSlots <= 256, "slot indices travel in one byte each");
@@ -699,7 +700,8 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
 template <bool kSubsample>
 static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, uint32_t ntips, const uint4 *quartets,
                                       int64_t m, uint64_t seed, double *d_rscor, uint2 *rstat, uint32_t *d_counts,
-                                      uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream)
+                                      uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream,
+                                      const uint32_t *d_skip = nullptr)
 {
     auto kern = resolve_mma_kernel<kSubsample, kNC, kNS>;
     const size_t smem = sizeof(MmaShared<kNC, kNS>);
@@ -711,10 +713,20 @@ static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, 
     const int64_t fv = g_mma_flush.load();
     const uint32_t flush_every = (fv >= 1 && fv < (int64_t)kMmaFlushEvery) ? (uint32_t)fv : kMmaFlushEvery;
     kern<<<grid, (kNC + kNS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank,
-                                                   d_status, flush_every);
+                                                   d_status, flush_every, d_skip);
     ++g_launches;
     g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
     return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_mma_full(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips, const uint32_t *d_quartets,
+                                    int64_t m, uint64_t seed, double *d_rscor, uint32_t *d_rstat, uint32_t *d_counts,
+                                    uint32_t *d_minrank, uint32_t *d_status, int num_sms, const uint32_t *d_skip,
+                                    cudaStream_t stream)
+{
+    return launch_resolve_mma<false>(plan, reinterpret_cast<const uint4 *>(d_planes), (uint32_t)ntips,
+                                     reinterpret_cast<const uint4 *>(d_quartets), m, seed, d_rscor, reinterpret_cast<uint2 *>(d_rstat),
+                                     d_counts, d_minrank, d_status, num_sms, stream, d_skip);
 }
 
 cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips,
@@ -734,7 +746,7 @@ cudaError_t launch_resolve(const PlanDev &plan, const uint32_t *d_planes, int64_
     const int force = g_kernel_choice.load();
     if (!subsample && (force == 5 || (force == 0 && pairgemm_applies(ntips, m, num_sms))))
         return launch_resolve_pairgemm(plan, d_planes, ntips, d_quartets, m, seed, d_rscor, d_rstat, d_counts, d_minrank,
-                                       d_status, num_sms, stream);
+                                       d_status, num_sms, force, stream);
     const bool use_mma = force ? (force == 3 || force == 5) : (m >= (int64_t)num_sms * 16);
     if (use_mma)
         return subsample ? launch_resolve_mma<true>(plan, planes, (uint32_t)ntips, quartets, m, seed, d_rscor, rstat, d_counts,
