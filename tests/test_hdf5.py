@@ -118,6 +118,43 @@ def test_reads_v2_headers_links_and_chunked_deflate(tmp_path):
         assert f["snps"].attrs["names"].tolist() == [b"tip_a", b"tip_b"]
 
 
+def test_reads_a_libhdf5_written_file():
+    """The one file in this image that libhdf5 itself wrote: scipy's MATLAB v7.3 test file (BSD-licensed test data, copied
+    to tests/golden/): 512-byte user block, superblock v0 with base address 512, symbol-table root group (v1 B-tree, local
+    heap, SNOD), v1 object header, contiguous little-endian f64 dataset, v1 attribute with a fixed-length string."""
+    from pathlib import Path
+    path = Path(__file__).parent / "golden" / "libhdf5_matlab73_testdouble.mat"
+    with hdf5.File(path, "r") as f:
+        assert f.keys() == ["testdouble"]
+        d = f["testdouble"]
+        assert d.shape == (9, 1) and d.dtype == np.float64
+        assert np.array_equal(d[:].ravel(), np.linspace(0, 2 * np.pi, 9))     # scipy's own expectation for this file
+        assert bytes(d.attrs["MATLAB_class"]) == b"double"
+
+
+def test_variable_length_string_names(tmp_path):
+    """``names`` stored the way h5py stores a ``list[str]``: variable-length UTF-8 strings in a global heap collection
+    (the reference reads them with ``i.decode() if isinstance(i, bytes) else i``, write_database.py:66-69)."""
+    names = ["tip_a", "tïp_β", "", "a_rather_longer_tip_name_that_spans_more_than_sixteen_bytes"]
+    path = tmp_path / "v.hdf5"
+    with hdf5.File(path, "w") as f:
+        ds = f.create_dataset("snps", data=np.arange(12, dtype=np.uint8).reshape(4, 3))
+        ds.attrs["names"] = np.array(names, dtype=object)
+        ds.attrs["version"] = np.int64(3)
+        f.create_dataset("snpsmap", data=np.zeros((3, 5), np.uint32)).attrs["columns"] = np.array(["a", "bc"], dtype=object)
+    raw = path.read_bytes()
+    g = raw.index(b"GCOL")
+    assert raw[g + 4] == 1 and struct.unpack_from("<Q", raw, g + 8)[0] == 4096      # one minimum-size collection
+    with hdf5.File(path, "r") as f:
+        got = f["snps"].attrs["names"]
+        assert got.dtype == object and got.tolist() == names
+        assert int(np.asarray(f["snps"].attrs["version"]).ravel()[0]) == 3
+        assert f["snpsmap"].attrs["columns"].tolist() == ["a", "bc"]
+        assert (f["snps"][:] == np.arange(12, dtype=np.uint8).reshape(4, 3)).all()
+    snps, snpsmap, got_names = database.read_snps_input(path)            # the input reader the CLI uses
+    assert got_names == names and snps.shape == (4, 3) and snpsmap.shape == (3, 5)
+
+
 def test_unsupported_features_fail_loudly(tmp_path):
     with pytest.raises(ValueError):
         p = tmp_path / "junk.hdf5"

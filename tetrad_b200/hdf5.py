@@ -13,17 +13,22 @@ What it does (HDF5 File Format Specification 3.0):
   as symbol tables or as compact link messages; layouts compact / contiguous / chunked with a v1
   B-tree index (layout v3) or a single chunk / implicit / fixed-array index (layout v4); the
   ``deflate`` and ``shuffle`` filters; fixed-point, floating-point and fixed-length string types;
-  attributes v1-v3 with fixed-size types.
-* not supported (raises ``NotImplementedError``): variable-length types, dense (fractal-heap)
+  attributes v1-v3 with fixed-size types or variable-length strings (global heap; what h5py writes for a
+  ``list[str]`` such as ``names``); a user block in front of the superblock.
+* not supported (raises ``NotImplementedError``): variable-length sequences, dense (fractal-heap)
   attribute or link storage, extensible-array / v2-B-tree chunk indexes, external links.
 
 The API mirrors the few h5py calls the code base makes: ``File(path, mode)`` as a context
 manager, ``f[name][:]``, ``name in f``, ``f.keys()``, ``f[name].shape/.dtype/.attrs``,
 ``f.create_dataset(name, data=...)`` and ``dset.attrs[key] = array``.
 
-Validation status: written files are re-read by this module (tests/test_hdf5.py); no libhdf5 is
-available in the image to cross-check against, so prefer h5py whenever it is installed
-(``tetrad_b200/database.py`` does).
+Validation status: the reader is checked against the one libhdf5-written file this image holds (scipy's MATLAB
+v7.3 test file, copied to ``tests/golden/libhdf5_matlab73_testdouble.mat``: user block, superblock v0, symbol-table
+group, v1 object header, contiguous f64 data, fixed-length string attribute -- the structures an h5py file written
+with default settings has; that file found the reader's one real defect, addresses not rebased past a user block).
+Chunked / filtered datasets, v2 headers and variable-length strings are read from files assembled by the tests from
+the format specification, not by libhdf5; written files are re-read by this module.  Prefer h5py whenever it is
+installed (``tetrad_b200/database.py`` does).
 """
 from __future__ import annotations
 
@@ -37,6 +42,20 @@ SIGNATURE = b"\x89HDF\r\n\x1a\n"
 UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
+class _VlenStr:
+    """Marker for the variable-length string datatype (class 9, type 1); elements are 16-byte global-heap references."""
+    itemsize = 16
+
+    def __init__(self, utf8: bool):
+        self.utf8 = utf8
+
+    def __repr__(self):
+        return f"vlen-str({'utf-8' if self.utf8 else 'ascii'})"
+
+
+_VLEN_STR_UTF8, _VLEN_STR_ASCII = _VlenStr(True), _VlenStr(False)
+
+
 # =============================================================================================
 # reading
 # =============================================================================================
@@ -48,7 +67,13 @@ class _Reader:
             pos = 512 if pos == 0 else pos * 2
             if pos + 8 > len(buf):
                 raise ValueError("not an HDF5 file")
+        # A file with a user block (MATLAB v7.3 files, ``h5py.File(userblock_size=...)``) has its superblock at 512, 1024,
+        # ...; every address in it is relative to the base address, which libhdf5 takes to be the superblock's own
+        # position (H5F__super_read adjusts ``base_addr`` to the address it found the signature at).
         self.base = pos
+        if pos:
+            buf = self.buf = buf[pos:]
+            pos = 0
         version = buf[pos + 8]
         if version in (0, 1):
             self.so, self.sl = buf[pos + 13], buf[pos + 14]
@@ -186,8 +211,39 @@ class _Reader:
         if cls == 3:
             return np.dtype(f"S{size}")
         if cls == 9:
-            raise NotImplementedError("variable-length datatypes (store names as fixed-length bytes)")
+            if (bits0 & 0x0F) == 1:                              # variable-length STRING: what h5py writes for list[str]
+                return _VLEN_STR_UTF8 if (data[2] & 0x0F) == 1 else _VLEN_STR_ASCII
+            raise NotImplementedError("variable-length sequence datatypes")
         raise NotImplementedError(f"datatype class {cls}")
+
+    def _vlen_strings(self, raw: bytes, count: int, utf8: bool) -> np.ndarray:
+        """``count`` variable-length strings: each element is {u32 length, global-heap collection address, u32 object
+        index}; the bytes live in a global heap collection (``GCOL``, spec III.E).  Returned like h5py does: an object
+        array of ``str`` (UTF-8) or ``bytes`` (ASCII)."""
+        out = np.empty(count, dtype=object)
+        for i in range(count):
+            length, addr, index = struct.unpack_from("<IQI", raw, 16 * i)
+            if length == 0 or addr in (0, UNDEF):
+                b = b""
+            else:
+                b = bytes(self._global_heap_object(addr, index)[:length])
+            out[i] = b.decode("utf-8") if utf8 else b
+        return out
+
+    def _global_heap_object(self, addr: int, index: int) -> bytes:
+        buf = self.buf
+        if buf[addr:addr + 4] != b"GCOL":
+            raise ValueError("bad global heap collection")
+        end = addr + struct.unpack_from("<Q", buf, addr + 8)[0]
+        p = addr + 16
+        while p + 16 <= end:
+            idx, _ref, _res, size = struct.unpack_from("<HHIQ", buf, p)
+            if idx == 0:                                         # free space: nothing follows
+                break
+            if idx == index:
+                return buf[p + 16:p + 16 + size]
+            p += 16 + (size + 7) // 8 * 8
+        raise KeyError(f"global heap object {index} not found")
 
     def dataspace(self, data: bytes):
         version, rank, flags = data[0], data[1], data[2]
@@ -248,7 +304,10 @@ class _Reader:
         dtype = self.dtype(data[p:p + tsize]); p += pad(tsize)
         shape = self.dataspace(data[p:p + ssize]); p += pad(ssize)
         count = int(np.prod(shape)) if shape else 1
-        value = np.frombuffer(data, dtype=dtype, count=count, offset=p)
+        if dtype is _VLEN_STR_UTF8 or dtype is _VLEN_STR_ASCII:
+            value = self._vlen_strings(data[p:p + 16 * count], count, dtype is _VLEN_STR_UTF8)
+        else:
+            value = np.frombuffer(data, dtype=dtype, count=count, offset=p)
         return name, (value.reshape(shape) if shape else value[0])
 
     def read(self, shape, dtype, layout: bytes, filters) -> np.ndarray:
@@ -458,12 +517,58 @@ def _object_header(messages) -> bytes:
     return struct.pack("<BBHII", 1, 0, len(messages), 1, len(body)) + b"\0\0\0\0" + body
 
 
-def _attribute_msg(name: str, value) -> bytes:
+class _GlobalHeap:
+    """One global heap collection (spec III.E) holding the bytes of every variable-length string of the file."""
+
+    def __init__(self):
+        self.addr = 0
+        self.objects = []
+
+    def add(self, b: bytes) -> int:
+        self.objects.append(b)
+        return len(self.objects)                                  # object indices start at 1
+
+    def size(self) -> int:
+        used = 16 + sum(16 + len(b) + (-len(b) % 8) for b in self.objects) + 16      # header, objects, free-space object
+        return max(4096, used + (-used % 8))
+
+    def tobytes(self) -> bytes:
+        total = self.size()
+        out = bytearray(total)
+        out[0:4] = b"GCOL"
+        struct.pack_into("<BBBBQ", out, 4, 1, 0, 0, 0, total)
+        p = 16
+        for i, b in enumerate(self.objects):
+            struct.pack_into("<HHIQ", out, p, i + 1, 1, 0, len(b))
+            out[p + 16:p + 16 + len(b)] = b
+            p += 16 + len(b) + (-len(b) % 8)
+        struct.pack_into("<HHIQ", out, p, 0, 0, 0, total - p)    # object 0: the free space, header included
+        return bytes(out)
+
+
+def _is_vlen_value(value) -> bool:
+    value = np.asarray(value)
+    return value.dtype.kind == "O" and all(isinstance(v, (str, bytes)) for v in value.ravel())
+
+
+def _attribute_msg(name: str, value, gheap: "_GlobalHeap | None" = None) -> bytes:
     value = np.asarray(value)
     if value.dtype.kind == "U":
         value = np.char.encode(value, "utf-8")
     if value.dtype.kind == "O":
-        raise TypeError("object arrays cannot be stored; encode strings to bytes first")
+        # list[str] as h5py stores it: variable-length UTF-8 strings, 16-byte global-heap references in the message
+        if gheap is None or not _is_vlen_value(value):
+            raise TypeError("object arrays other than lists of str/bytes cannot be stored")
+        nm = name.encode("utf-8") + b"\0"
+        base = struct.pack("<BBBBI", 0x10 | 3, 0x10, 0, 0, 1)     # base type: 1-byte string
+        dt = struct.pack("<BBBBI", 0x10 | 9, 0x01, 0x01, 0, 16) + base   # class 9, type = string, charset UTF-8
+        ds = _dataspace_msg(value.shape)
+        body = b""
+        for v in value.ravel():
+            b = v.encode("utf-8") if isinstance(v, str) else bytes(v)
+            body += struct.pack("<IQI", len(b), gheap.addr, gheap.add(b))
+        head = struct.pack("<BBHHH", 1, 0, len(nm), len(dt), len(ds))
+        return _message(0x0C, head + _pad8(nm) + _pad8(dt) + _pad8(ds) + body)
     value = np.ascontiguousarray(value).astype(value.dtype.newbyteorder("<"), copy=False)
     nm = name.encode("utf-8") + b"\0"
     dt, ds = _datatype_msg(value.dtype), _dataspace_msg(value.shape)
@@ -501,6 +606,18 @@ def _write_file(path: Path, datasets: dict) -> None:
         snod_addrs.append(pos)
         pos += snod_size
 
+    gheap = _GlobalHeap()
+    nvlen = sum(1 for name in names for v in datasets[name].attrs.values() if _is_vlen_value(v))
+    if nvlen:
+        for name in names:                                       # size the collection before anything refers to it
+            for v in datasets[name].attrs.values():
+                if _is_vlen_value(v):
+                    for x in np.asarray(v).ravel():
+                        gheap.add(x.encode("utf-8") if isinstance(x, str) else bytes(x))
+        gheap.addr = pos
+        pos += gheap.size()
+        gheap.objects = []                                       # refilled, in the same order, by _attribute_msg
+
     blobs, headers = {}, {}
     for name in names:
         ds = datasets[name]
@@ -513,7 +630,7 @@ def _write_file(path: Path, datasets: dict) -> None:
         pos += len(raw) + (-len(raw) % 8)
         msgs = [_message(0x01, _dataspace_msg(data.shape)), _message(0x03, _datatype_msg(data.dtype)),
                 _message(0x08, struct.pack("<BBQQ", 3, 1, data_addr if raw else UNDEF, len(raw)))]
-        msgs += [_attribute_msg(k, v) for k, v in ds.attrs.items()]
+        msgs += [_attribute_msg(k, v, gheap) for k, v in ds.attrs.items()]
         hdr = _object_header(msgs)
         headers[name] = (pos, hdr)
         pos += len(hdr) + (-len(hdr) % 8)
@@ -545,6 +662,9 @@ def _write_file(path: Path, datasets: dict) -> None:
         struct.pack_into("<BBH", out, saddr + 4, 1, 0, len(grp))
         for i, name in enumerate(grp):
             struct.pack_into("<QQII", out, saddr + 8 + i * 40, name_off[name], headers[name][0], 0, 0)
+    if nvlen:
+        blob = gheap.tobytes()
+        out[gheap.addr:gheap.addr + len(blob)] = blob
     for name in names:
         addr, hdr = headers[name]
         out[addr:addr + len(hdr)] = hdr
