@@ -145,7 +145,11 @@ int tq_boot_pack_rows(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntip
  * subsample != 0 -> one SNP per locus (subsample_chunk_to_matrices); 0 -> all SNPs
  * (full_chunk_to_matrices; chunks of the list whose quartets fill the tiles of a tip-pair grid densely -- exhaustive
  * lists and contiguous ranges of them -- go through one u8 GEMM over tip pairs on tcgen05.mma, decided on the device).  Tip indices must be < ntips (checked on the device: offending
- * quartets get best = 0xFFFFFFFF and the call's status word, if given, is set non-zero).
+ * quartets get best = 0xFFFFFFFF and word 0 of the call's status block, if given, is set non-zero).
+ * d_status: NULL or u32[4], zeroed by the caller.  [0] bit 0 = some quartet had a tip index out of range; [1..3] are
+ *   written only after tq_set_option("stack_stats", 1): diagnostics of the tensor-core kernel in subsample mode, summed
+ *   over the quartets (wrapping): tile products taken, tiles stacked on earlier ones, and loci counted one by one (the
+ *   busiest lane's share) -- see "stack_fill" below.
  */
 int tq_resolve(const tq_plan *plan, const uint32_t *d_planes, int64_t ntips,
                const uint32_t *d_quartets, int64_t m, int subsample, uint64_t seed,
@@ -215,6 +219,10 @@ int64_t tq_launch_count(void);
  * ("tq::resolve_mma_kernel<true>", ...); a static string, never NULL */
 const char *tq_last_kernel(void);
 
+/* count warps per CTA (of 16; the others score) of the last tensor-core resolve launch: the launcher picks the mix from
+ * the plan's tiles and rank chunks per tip row (8 + 8 at the C2 shape, 12 + 4 at C3 / C4 / C5); 0 before the first launch */
+int tq_last_count_warps(void);
+
 /* Full mode routes every chunk (2^18 quartets) of a list on the device: to the tip-pair GEMM when its tiles are dense
  * (>= 30 quartets per 128-quartet tile, all tips ascending), to the per-quartet kernel otherwise.  out[0] / out[1] =
  * chunks routed to the GEMM / to the per-quartet kernel since the library was loaded (read after synchronising). */
@@ -226,6 +234,16 @@ int tq_pairgemm_stats(int64_t out[2]);
  *                      launch runs 3)
  *   "mma_flush_every"  > 0: tile products between accumulator flushes of the tensor-core kernel
  *                      (default 16384; tests lower it to reach the flush path), 0 = default
+ *   "stack_fill"       subsample mode stacks the merged planes of consecutive sparse tiles in one tile copy and takes ONE
+ *                      tile product when this percentage of its 1024 bit slots is filled: -1 = default (85),
+ *                      0 = one product per tile (never stack), 1..100
+ *   "stack_ovf"        a tile is stacked on the previous ones only if no lane has more than this many selected loci
+ *                      whose bit slot is already taken (those are counted one by one, by shared-memory atomics);
+ *                      otherwise the stack is multiplied out first.  0..32, default 6
+ *   "stack_stats"      != 0: the tensor-core kernel adds its stacking diagnostics to words 1..3 of the status block
+ *                      (default 0: off)
+ *   "count_warps"      count warps per CTA of the tensor-core kernel (of 16; the others score): 0 = chosen from the
+ *                      plan (default: 8 at the C2 shape, 12 where a tip row has a hundred tiles or more), 8, 12
  * Returns TQ_EINVAL for an unknown name or an out-of-range value. */
 int tq_set_option(const char *name, int64_t value);
 

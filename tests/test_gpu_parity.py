@@ -308,6 +308,53 @@ def test_more_than_63_tiles_exercises_the_counter_flush(tb, oracle, kernel, sub)
     assert (minrank.cpu().numpy() == det["minrank"]).all()
 
 
+@pytest.mark.parametrize("count_warps", [8, 12])
+def test_stacked_tiles_count_every_locus_once(tb, oracle, count_warps):
+    """Subsample mode stacks the merged planes of consecutive sparse tiles before one tile product; loci whose bit slot
+    is taken are counted by shared-memory atomics.  Whatever the stacking limits (never / only without collisions / the
+    defaults / everything, i.e. hundreds of loci through the atomics) and whatever the count / score warp mix, the counts
+    are the oracle's and all results are the same bits; the diagnostics in the status block show the paths were taken."""
+    from tetrad_b200 import _lib, synth
+    lib = _lib.load()
+    d = synth.generate(9, 30_000, 90_000, seed=23)                  # ~30 tiles, a third of the loci selected
+    db = synth.prepare_database(d.snps, d.snpsmap, seed=23)
+    from itertools import combinations
+    quartets = np.array(list(combinations(range(9), 4)), dtype=np.uint32)
+    eng = tb.QuartetResolver(device=0).load(db["tmparr"], db["tmpmap"])
+    _, ostat, oscor, det = oracle.new_infer_resolved_quartets(db["tmparr"], db["tmpmap"], quartets[::6], True, return_details=True)
+    outs, stats = [], []
+    try:
+        _lib.set_kernel("mma")
+        _lib.check(lib.tq_set_option(b"count_warps", count_warps))
+        _lib.check(lib.tq_set_option(b"stack_stats", 1))
+        for fill, ovf in ((0, 0), (85, 0), (-1, 6), (100, 32), (40, 3)):
+            _lib.check(lib.tq_set_option(b"stack_fill", fill))
+            _lib.check(lib.tq_set_option(b"stack_ovf", ovf))
+            rstat, rscor, counts, minrank = eng.resolve(quartets, True, want_counts=True)
+            outs.append((rstat.cpu().numpy().copy(), rscor.cpu().numpy().copy(), counts.cpu().numpy().copy(), minrank.cpu().numpy().copy()))
+            stats.append(eng._last_status.cpu().numpy().astype(np.int64) & 0xFFFFFFFF)
+            assert lib.tq_last_count_warps() == count_warps
+    finally:
+        _lib.set_kernel("auto")
+        for name, val in ((b"count_warps", 0), (b"stack_fill", -1), (b"stack_ovf", 6), (b"stack_stats", 0)):
+            _lib.check(lib.tq_set_option(name, val))
+    got = outs[0][2].view(np.uint32).reshape(-1, 16, 16)
+    assert (got[::6] == det["mats"][:, 0]).all() and (outs[0][0].view(np.uint32)[::6] == ostat).all()
+    assert_scores_close(outs[0][1][::6], oscor, ostat[:, 1])
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert a.tobytes() == b.tobytes()
+    ntiles, m = eng.info["ntiles"], len(quartets)
+    assert stats[0][1] == ntiles * m and stats[0][2] == 0 and stats[0][3] == 0        # never stacked: one product per tile
+    assert stats[1][3] == 0 and stats[1][1] + stats[1][2] == ntiles * m               # stacked only without collisions
+    assert stats[3][1] < stats[2][1] < stats[0][1]                                     # more stacking, fewer products
+    assert stats[3][3] > stats[2][3] > 0                                               # ... and more loci through the atomics
+    with pytest.raises(_lib.TetradB200Error):
+        _lib.check(lib.tq_set_option(b"count_warps", 10))
+    with pytest.raises(_lib.TetradB200Error):
+        _lib.check(lib.tq_set_option(b"stack_ovf", 33))
+
+
 def test_c3_shape_random_quartets_sampled_parity(tb, oracle):
     """BASELINE config C3 shape (100 tips, 100 000 loci, 500 000 SNPs): a sample of random quartets,
     unranked on the device from the reference's rng.choice draw, exact against the oracle."""

@@ -103,6 +103,8 @@ def _declare(lib):
     lib.tq_launch_count.argtypes = []
     lib.tq_last_kernel.restype = c.c_char_p
     lib.tq_last_kernel.argtypes = []
+    lib.tq_last_count_warps.restype = i32
+    lib.tq_last_count_warps.argtypes = []
     lib.tq_pairgemm_stats.restype = i32
     lib.tq_pairgemm_stats.argtypes = [c.POINTER(i64)]
     lib.tq_set_option.restype = i32
@@ -156,7 +158,7 @@ def _declare(lib):
 
 
 EXPORTS = [
-    "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_set_option", "tq_pairgemm_stats", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank", "tq_sample_quartets", "tq_sample_ranks_host",
+    "tq_version", "tq_last_error", "tq_launch_count", "tq_last_kernel", "tq_last_count_warps", "tq_set_option", "tq_pairgemm_stats", "tq_plan_create", "tq_plan_create_runs", "tq_boot_pack", "tq_unrank", "tq_sample_quartets", "tq_sample_ranks_host",
     "tq_plan_destroy",
     "tq_plan_info", "tq_plan_tables", "tq_pack", "tq_pack_rows", "tq_boot_pack_rows", "tq_resolve", "tq_ctx_create", "tq_ctx_destroy", "tq_resolve_host",
     "tq_ctx_last_traffic", "tq_microbench", "tq_format_tsv", "tq_round_scores", "tq_format_qmc", "tq_format_qmc_rows", "tq_qmc_weights",

@@ -130,6 +130,7 @@ const char *tq_last_error(void) { return g_err; }
 
 int64_t tq_launch_count(void) { return tq::g_launches.load(); }
 const char *tq_last_kernel(void) { return tq::g_last_kernel.load(); }
+int tq_last_count_warps(void) { return tq::g_last_count_warps.load(); }
 
 int tq_pairgemm_stats(int64_t out[2])
 {
@@ -150,6 +151,26 @@ int tq_set_option(const char *name, int64_t value)
     if (!strcmp(name, "mma_flush_every")) {
         if (value < 0) return fail(TQ_EINVAL, "tq_set_option: mma_flush_every must be >= 0");
         tq::g_mma_flush = value;
+        return TQ_OK;
+    }
+    if (!strcmp(name, "stack_fill")) {
+        if (value < -1 || value > 100) return fail(TQ_EINVAL, "tq_set_option: stack_fill must be -1 (default) or 0..100 (percent)");
+        tq::g_stack_fill = (int)value;
+        return TQ_OK;
+    }
+    if (!strcmp(name, "stack_stats")) {
+        tq::g_stack_stats = value != 0;
+        return TQ_OK;
+    }
+    if (!strcmp(name, "stack_ovf")) {
+        if (value < 0 || value > 32) return fail(TQ_EINVAL, "tq_set_option: stack_ovf must be 0..32");
+        tq::g_stack_ovf = (int)value;
+        return TQ_OK;
+    }
+    if (!strcmp(name, "count_warps")) {
+        if (value != 0 && value != 8 && value != 12)
+            return fail(TQ_EINVAL, "tq_set_option: count_warps must be 0 (by the plan), 8 or 12");
+        tq::g_count_warps = (int)value;
         return TQ_OK;
     }
     return fail(TQ_EINVAL, "tq_set_option: unknown option");

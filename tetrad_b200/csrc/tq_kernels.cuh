@@ -65,5 +65,10 @@ extern std::atomic<int64_t> g_launches;      // kernels launched by this library
 extern std::atomic<int> g_kernel_choice;          // 0 by launch size and mode, 1 fused POPC, 3 tensor-core count, 5 tip-pair GEMM (full mode)
 extern std::atomic<int64_t> g_mma_flush;          // > 0: tile products between accumulator flushes of the tensor-core kernel (tests)
 extern std::atomic<const char *> g_last_kernel;   // name of the resolve kernel variant launched last
+extern std::atomic<int> g_count_warps;            // 0 by the plan; else count warps per CTA of the tensor-core kernel (of 16)
+extern std::atomic<int> g_stack_fill;             // < 0 default; else percent of a tile's bit slots filled before a stacked product (0: never stack)
+extern std::atomic<int> g_stack_ovf;              // most overflow loci a lane may have for a tile to be stacked on the previous ones
+extern std::atomic<int> g_stack_stats;            // != 0: stacking diagnostics are added to status[1..3]
+extern std::atomic<int> g_last_count_warps;       // count warps per CTA of the last tensor-core launch
 
 }  // namespace tq

@@ -42,6 +42,7 @@ namespace tq {
 
 std::atomic<int64_t> g_launches{0};
 std::atomic<const char *> g_last_kernel{"none"};
+std::atomic<int> g_last_count_warps{0};          // count warps per CTA of the last tensor-core launch
 // Kernel choice and test hooks (tq_set_option in the C ABI; the environment gives the initial values).
 //   g_kernel_choice: 0 = by launch size and mode, 1 = fused (one warp per quartet, POPC), 3 = tensor-core count,
 //                    5 = tip-pair GEMM (full mode only; subsample launches run 3)
@@ -56,8 +57,37 @@ static int64_t initial_mma_flush()
     const char *e = getenv("TQ_MMA_FLUSH");
     return e ? atol(e) : 0;
 }
+static int initial_count_warps()
+{
+    const char *e = getenv("TQ_COUNT_WARPS");
+    return e ? atoi(e) : 0;
+}
 std::atomic<int> g_kernel_choice{initial_kernel_choice()};
 std::atomic<int64_t> g_mma_flush{initial_mma_flush()};
+static int initial_stack_fill()
+{
+    const char *e = getenv("TQ_STACK_FILL");
+    return e ? atoi(e) : -1;
+}
+std::atomic<int> g_stack_fill{initial_stack_fill()};     // < 0: default; else percent of a tile's 1024 bit slots (0: never stack)
+static int initial_stack_ovf()
+{
+    const char *e = getenv("TQ_STACK_OVF");
+    return e ? atoi(e) : 6;
+}
+std::atomic<int> g_stack_ovf{initial_stack_ovf()};
+std::atomic<int> g_stack_stats{0};                       // != 0: the kernel adds its stacking diagnostics to status[1..3]       // most overflow loci a lane may have for a tile to be stacked
+std::atomic<int> g_count_warps{initial_count_warps()};
+
+// Bit slots of P that must be filled before the stacked tiles' product is taken (count_quartet_mma).
+static constexpr int kStackFillPercent = 85;
+static uint32_t stack_fill_slots()
+{
+    const int pct = g_stack_fill.load();
+    return (uint32_t)((pct < 0 ? kStackFillPercent : pct > 100 ? 100 : pct) * kTileLoci / 100) |
+           (g_stack_stats.load() ? 0x80000000u : 0u);
+}
+   // 0: by the plan; else the count warps per CTA of the tensor-core kernel
 
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 static constexpr int kWarps = 4;                 // warps (= quartets in flight) per CTA of the fused kernel
@@ -384,7 +414,14 @@ static constexpr int kScales = 4;
 static constexpr int kPStride = 34;                 // words per plane row of the per-warp tile copy
 static constexpr uint32_t kMmaFlushEvery = 16384;   // tile products between accumulator flushes: 16384 * 1024 * 4^3 < 2^31
                                                     // (tq_set_option("mma_flush_every") lowers it so that tests reach the flush)
-static constexpr int kNC = 8, kNS = 8;              // count / score warps per CTA (measured mixes: profiles/r01_v7_resolve_ncu.md)
+static constexpr int kMmaWarps = 16;                // warps per CTA: 16 x 32 threads x 128 registers = the SM's register file
+// Count / score warps per CTA.  The FP64 scores cost the same for every quartet while the count work grows with the tiles
+// and rank chunks of a tip row, so the mix follows the plan (pick_count_warps): 8 + 8 at the C2 shape (49 tiles: the two
+// sides balance, profiles/r01_v7_resolve_ncu.md), 12 + 4 where a row has a hundred tiles or more and eight score warps
+// would idle on half of the registers (C3 / C4 / C5: +7 .. +10 %).  Warp w runs on scheduler w % 4, so only multiples of
+// four keep the four schedulers evenly loaded: 10 + 6, 11 + 5, 13 + 3 and 14 + 2 all measured slower than both
+// neighbours, and 16 homogeneous warps (count, then score the same quartet) slower than 12 + 4 (profiles/r02_warp_mix.md).
+static constexpr int kMixes[] = {8, 12};            // count warps of the instantiated kernels (score warps: the rest)
 
 __device__ __forceinline__ void imma_u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
@@ -408,11 +445,11 @@ __device__ __forceinline__ MmaLanePtrs mma_lane_ptrs(uint32_t *P, int lane)
     return lp;
 }
 
-__device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
-                                               const uint32_t (&MC)[4], const uint32_t (&MD)[4],
-                                               const MmaLanePtrs &lp, int (&acc)[kScales][2][4])
+// This lane's word of the 16 planes -> the warp's tile copy P (plain store: whatever P held is replaced).
+__device__ __forceinline__ void store_tile_planes(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                                  const uint32_t (&MC)[4], const uint32_t (&MD)[4], const MmaLanePtrs &lp)
 {
-    __syncwarp();                                    // the previous tile's reads are over
+    __syncwarp();                                    // the previous tile product's reads are over
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         lp.st[(0 + k) * kPStride] = MA[k];
@@ -420,7 +457,12 @@ __device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const ui
         lp.st[(8 + k) * kPStride] = MC[k];
         lp.st[(12 + k) * kPStride] = MD[k];
     }
-    __syncwarp();
+}
+
+// The 16 x 16 x 1024 product of the planes in P, added to the accumulators.
+__device__ __forceinline__ void tile_product_mma(const MmaLanePtrs &lp, int (&acc)[kScales][2][4])
+{
+    __syncwarp();                                    // every lane's stores to P are visible
     const uint32_t *pa = lp.pa, *pb = lp.pb;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -444,6 +486,93 @@ __device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const ui
                 imma_u8(acc[v][0], f0, f1, f2, f3, y[s][0] & msk, y[s][1] & msk);
                 imma_u8(acc[v][1], f0, f1, f2, f3, y[s][2] & msk, y[s][3] & msk);
             }
+    }
+}
+
+__device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                               const uint32_t (&MC)[4], const uint32_t (&MD)[4],
+                                               const MmaLanePtrs &lp, int (&acc)[kScales][2][4])
+{
+    store_tile_planes(MA, MB, MC, MD, lp);
+    tile_product_mma(lp, acc);
+}
+
+// ---- stacking sparse tiles (subsample mode) ------------------------------------------------------------------------
+// A tile product costs the same whether 1 024 or 100 of the tile's loci selected a column, and on real and synthetic
+// data most loci select none for a given quartet (a column must be complete in all four tips and segregating: ~36 % of the
+// loci at the BASELINE shapes).  Bit positions carry no meaning once the planes are merged, so the merged planes of
+// SEVERAL tiles are stacked in P before one product is taken: a selected locus whose bit slot is still free (`put`) is
+// OR-ed into P; one whose slot is taken (`ovf`) is counted on the spot by a shared-memory atomic on its pattern index.
+// The product runs when the slots filled reach `stack_fill` (a warp-wide popcount per tile decides), so dense data
+// behaves as before (one product per tile, no overflow) and sparse data takes a fraction of the products.  Every selected
+// column is counted exactly once, by the product or by the atomic: the counts stay bit-exact.
+__device__ __forceinline__ void merge_tile_planes(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                                  const uint32_t (&MC)[4], const uint32_t (&MD)[4], uint32_t put,
+                                                  const MmaLanePtrs &lp)
+{
+    __syncwarp();                                    // the previous tile product's reads are over
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        lp.st[(0 + k) * kPStride] |= MA[k] & put;
+        lp.st[(4 + k) * kPStride] |= MB[k] & put;
+        lp.st[(8 + k) * kPStride] |= MC[k] & put;
+        lp.st[(12 + k) * kPStride] |= MD[k] & put;
+    }
+}
+
+// Count the selected loci in `ovf` (bit slots already taken in P) one by one: pattern index ((a*4+b)*4+c)*4+d from the
+// one-hot planes (A, C, G, T = 0..3: low bit = C | T, high bit = G | T), one shared-memory atomic each.
+// The kernel is bound by the port the ALU pipe shares with the legacy IMMA (LOP3 / SHF / IMMA of the other count warps),
+// while the FMA pipe idles: the eight code bits of a locus are therefore pulled out with integer MULTIPLIES -- w * 2^(31-pos)
+// puts bit `pos` on top, mul.hi by 2 brings it down to 0/1, mad.lo chains them -- and `two` is a kernel argument so that ptxas
+// cannot turn the multiplies back into ALU-pipe shifts.
+__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ void scatter_overflow(uint32_t ovf, const uint32_t (&MA)[4], const uint32_t (&MB)[4],
+                                                 const uint32_t (&MC)[4], const uint32_t (&MD)[4], uint32_t *T, uint32_t two)
+{
+    const uint32_t la = MA[1] | MA[3], ha = MA[2] | MA[3], lb = MB[1] | MB[3], hb = MB[2] | MB[3];
+    const uint32_t lc = MC[1] | MC[3], hc = MC[2] | MC[3], ld = MD[1] | MD[3], hd = MD[2] | MD[3];
+    const uint32_t four = mul_lo(two, two), sixteen = mul_lo(four, four);
+    // two loci per trip (the highest and the lowest set bit): half the trips of the lane with the most overflow
+    while (ovf) {
+        const uint32_t pos = 31u - __clz(ovf);
+        ovf ^= 1u << pos;
+        const bool second = ovf != 0u;
+        const uint32_t pos2 = second ? (uint32_t)__ffs(ovf) - 1u : pos;
+        ovf &= ovf - 1u;
+        const uint32_t up = 0x80000000u >> pos, up2 = 0x80000000u >> pos2;      // 2^(31 - pos)
+        // bit `pos` of every code plane as 0 / 1, on the FMA pipe
+        const uint32_t b7 = mul_hi(mul_lo(ha, up), two), b6 = mul_hi(mul_lo(la, up), two);
+        const uint32_t b5 = mul_hi(mul_lo(hb, up), two), b4 = mul_hi(mul_lo(lb, up), two);
+        const uint32_t b3 = mul_hi(mul_lo(hc, up), two), b2 = mul_hi(mul_lo(lc, up), two);
+        const uint32_t b1 = mul_hi(mul_lo(hd, up), two), b0 = mul_hi(mul_lo(ld, up), two);
+        const uint32_t c7 = mul_hi(mul_lo(ha, up2), two), c6 = mul_hi(mul_lo(la, up2), two);
+        const uint32_t c5 = mul_hi(mul_lo(hb, up2), two), c4 = mul_hi(mul_lo(lb, up2), two);
+        const uint32_t c3 = mul_hi(mul_lo(hc, up2), two), c2 = mul_hi(mul_lo(lc, up2), two);
+        const uint32_t c1 = mul_hi(mul_lo(hd, up2), two), c0 = mul_hi(mul_lo(ld, up2), two);
+        const uint32_t idx = mad_lo(mad_lo(mad_lo(b7, two, b6), four, mad_lo(b5, two, b4)), sixteen,
+                                    mad_lo(mad_lo(b3, two, b2), four, mad_lo(b1, two, b0)));
+        const uint32_t idx2 = mad_lo(mad_lo(mad_lo(c7, two, c6), four, mad_lo(c5, two, c4)), sixteen,
+                                     mad_lo(mad_lo(c3, two, c2), four, mad_lo(c1, two, c0)));
+        atomicAdd(T + idx, 1u);
+        if (second) atomicAdd(T + idx2, 1u);
     }
 }
 
@@ -501,8 +630,9 @@ __device__ __forceinline__ void finish_tile_planes(uint32_t taken, uint32_t (&MA
 template <bool kSubsample>
 __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uint4 *__restrict__ planes,
                                                   uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane,
-                                                  uint32_t flush_every)
+                                                  uint32_t flush_every, uint32_t stack_fill, uint32_t stack_ovf, uint32_t two, uint32_t *stats)
 {
+    stack_fill &= 0x7FFFFFFFu;                        // the top bit asked for the diagnostics (`stats` is then non-null)
     static_assert((kMStages & (kMStages - 1)) == 0, "ring depth must be a power of two");
     int acc[kScales][2][4];
 #pragma unroll
@@ -532,8 +662,15 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
     uint32_t u = 0;                                   // rank-chunk index along the rows
     const int ntiles = plan.ntiles;
     uint32_t Knext = ntiles > 0 ? __ldg(plan.tile_k) : 0u;
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const uint32_t K = Knext;
+    uint32_t occ = 0u;                                // bit slots of P in use (subsample mode: stacked tiles)
+    bool stacked = false;                             // P holds planes that no product has taken yet (warp-uniform)
+    uint32_t n_products = 0u, n_stacked = 0u, n_walk = 0u;   // diagnostics: status[1..3]
+    // Subsample mode runs one extra, empty pass of the tile loop so that the product of the last stacked tiles is taken at
+    // the same (single) call site as every other product: the IMMA body is in the instruction stream once.
+    const int npasses = kSubsample ? ntiles + 1 : ntiles;
+    for (int tile = 0; tile < npasses; ++tile) {
+        const bool last = kSubsample && tile == ntiles;
+        const uint32_t K = last ? 0u : Knext;
         if (tile + 1 < ntiles) Knext = __ldg(plan.tile_k + tile + 1);
         uint32_t taken = 0u;
         uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
@@ -560,11 +697,37 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
         }
         if (kSubsample) {
             finish_tile_planes(taken, MA, MB, MC, MD);
-            count_tile_mma(MA, MB, MC, MD, lp, acc);
-            if (++pending == flush_every) { flush_mma(acc, T, lane); pending = 0; }
+            // The price of stacking this tile on the ones in P is known exactly: the lane with the most taken slots walks
+            // its overflow bit by bit.  Past `stack_ovf` loci, or once `stack_fill` slots are in use, the stack is
+            // multiplied out first and the tile starts a new one.
+            const uint32_t ovf = taken & occ;
+            const uint32_t worst = __reduce_max_sync(kFull, (uint32_t)__popc(ovf));
+            const uint32_t filled = __reduce_add_sync(kFull, (uint32_t)__popc(occ));
+            if (stacked && (last || worst > stack_ovf || filled >= stack_fill)) {
+                tile_product_mma(lp, acc);
+                ++n_products;
+                stacked = false;
+                if (++pending == flush_every) { __syncwarp(); flush_mma(acc, T, lane); pending = 0; }
+            }
+            if (last) break;
+            if (!stacked) {
+                store_tile_planes(MA, MB, MC, MD, lp);
+                occ = taken;
+                stacked = true;
+            } else {
+                merge_tile_planes(MA, MB, MC, MD, taken & ~occ, lp);
+                occ |= taken;
+                ++n_stacked;
+                n_walk += worst;
+                if (worst) scatter_overflow(ovf, MA, MB, MC, MD, T, two);
+            }
         }
     }
     cp_async_wait<0>();
+    if (kSubsample && stats && lane == 0) {
+        atomicAdd(stats + 1, n_products); atomicAdd(stats + 2, n_stacked); atomicAdd(stats + 3, n_walk);
+    }
+    __syncwarp();                                     // the overflow atomics on T precede the accumulators' flush
     flush_mma(acc, T, lane);
 }
 
@@ -596,7 +759,8 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
                    const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
                    double *__restrict__ rscor, uint2 *__restrict__ rstat,
                    uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
-                   uint32_t *__restrict__ status, uint32_t flush_every, const uint32_t *__restrict__ skip)
+                   uint32_t *__restrict__ status, uint32_t flush_every, uint32_t stack_fill, uint32_t stack_ovf, uint32_t two,
+                   const uint32_t *__restrict__ skip)
 {
     if (skip && skip[0]) return;                     // full mode: the tip-pair GEMM took this chunk (tq_pairgemm.cu)
     using Shared = MmaShared<NC, NS>;
@@ -641,7 +805,7 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
 #pragma unroll
             for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
             __syncwarp();
-            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every);
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every, stack_fill, stack_ovf, two, (stack_fill & 0x80000000u) ? status : nullptr);
             if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.full[slot]);
@@ -697,26 +861,60 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
     }
 }
 
+// Count warps for a plan.  Per quartet a count warp spends ~1 980 clocks per tile product (stage 2) and ~440 per rank
+// chunk (stage 1), a score warp ~190 000 clocks (phase clocks at C2, profiles/r01_v7_resolve_ncu.md); the count share of
+// the 16 warps is rounded to the nearest instantiated mix.  Full mode runs one tile product per rank chunk.
+static int pick_count_warps(const PlanDev &plan, bool subsample)
+{
+    const int forced = g_count_warps.load();
+    if (forced > 0) return forced >= 10 ? 12 : 8;
+    const double nchunks = (double)(plan.row_u4 / kTileWords);
+    const double products = subsample ? (double)plan.ntiles : nchunks;
+    const double count = 1980.0 * products + 440.0 * nchunks, score = 190000.0;
+    return count >= 1.5 * score ? 12 : 8;
+}
+
+template <bool kSubsample, int NC>
+static cudaError_t launch_resolve_mma_mix(const PlanDev &plan, const uint4 *planes, uint32_t ntips, const uint4 *quartets,
+                                          int64_t m, uint64_t seed, double *d_rscor, uint2 *rstat, uint32_t *d_counts,
+                                          uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream,
+                                          const uint32_t *d_skip)
+{
+    constexpr int NS = kMmaWarps - NC;
+    auto kern = resolve_mma_kernel<kSubsample, NC, NS>;
+    constexpr size_t smem = sizeof(MmaShared<NC, NS>);
+    static_assert(smem <= 227 * 1024, "warp mix does not fit in shared memory");
+    static SmemAttr attr;
+    cudaError_t e = attr.ensure(kern, smem);
+    if (e != cudaSuccess) return e;
+    const int64_t want = (m + NC - 1) / NC;
+    const unsigned grid = (unsigned)(want < num_sms ? want : num_sms);
+    const int64_t fv = g_mma_flush.load();
+    const uint32_t flush_every = (fv >= 1 && fv < (int64_t)kMmaFlushEvery) ? (uint32_t)fv : kMmaFlushEvery;
+    kern<<<grid, kMmaWarps * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank,
+                                                 d_status, flush_every, stack_fill_slots(), (uint32_t)g_stack_ovf.load(), 2u, d_skip);
+    ++g_launches;
+    g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
+    g_last_count_warps = NC;
+    return cudaGetLastError();
+}
+
 template <bool kSubsample>
 static cudaError_t launch_resolve_mma(const PlanDev &plan, const uint4 *planes, uint32_t ntips, const uint4 *quartets,
                                       int64_t m, uint64_t seed, double *d_rscor, uint2 *rstat, uint32_t *d_counts,
                                       uint32_t *d_minrank, uint32_t *d_status, int num_sms, cudaStream_t stream,
                                       const uint32_t *d_skip = nullptr)
 {
-    auto kern = resolve_mma_kernel<kSubsample, kNC, kNS>;
-    const size_t smem = sizeof(MmaShared<kNC, kNS>);
-    static SmemAttr attr;
-    cudaError_t e = attr.ensure(kern, smem);
-    if (e != cudaSuccess) return e;
-    const int64_t want = (m + kNC - 1) / kNC;
-    const unsigned grid = (unsigned)(want < num_sms ? want : num_sms);
-    const int64_t fv = g_mma_flush.load();
-    const uint32_t flush_every = (fv >= 1 && fv < (int64_t)kMmaFlushEvery) ? (uint32_t)fv : kMmaFlushEvery;
-    kern<<<grid, (kNC + kNS) * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank,
-                                                   d_status, flush_every, d_skip);
-    ++g_launches;
-    g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
-    return cudaGetLastError();
+#define TQ_MIX(NC)                                                                                                          \
+    case NC:                                                                                                                \
+        return launch_resolve_mma_mix<kSubsample, NC>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts,    \
+                                                      d_minrank, d_status, num_sms, stream, d_skip)
+    switch (pick_count_warps(plan, kSubsample)) {
+        TQ_MIX(12);
+    default:
+        TQ_MIX(8);
+    }
+#undef TQ_MIX
 }
 
 cudaError_t launch_resolve_mma_full(const PlanDev &plan, const uint32_t *d_planes, int64_t ntips, const uint32_t *d_quartets,
