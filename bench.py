@@ -254,7 +254,28 @@ def ncu_record(config: str, subsample: bool):
     return json.loads(path.read_text()) if path.exists() else None
 
 
-def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local, subsample=True, kernel=None):
+def stacking_stats(lib, engine, run_once, nq):
+    """One extra, untimed launch with the kernel's stacking diagnostics on (tq_set_option("stack_stats")): tile products
+    taken, tiles stacked on earlier ones and loci counted one by one (busiest lane), per quartet of this rank."""
+    from tetrad_b200 import _lib
+    import torch
+    _lib.check(lib.tq_set_option(b"stack_stats", 1))
+    try:
+        run_once()
+        torch.cuda.synchronize()
+        st = engine._last_status.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    finally:
+        _lib.check(lib.tq_set_option(b"stack_stats", 0))
+    if nq <= 0 or st[1] == 0:
+        return None
+    return {"tile_products_per_quartet": float(st[1]) / nq, "tiles_stacked_per_quartet": float(st[2]) / nq,
+            "overflow_walk_per_quartet": float(st[3]) / nq, "count_warps": int(lib.tq_last_count_warps()),
+            "note": "subsample mode stacks the merged planes of consecutive sparse tiles before ONE 16 x 16 x 1024 tile product; "
+                    "loci whose bit slot is taken are counted by shared-memory atomics (walk = the busiest lane's share); "
+                    "status words 1..3 of an extra untimed launch of the same shape (wrap at 2^32)"}
+
+
+def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local, subsample=True, kernel=None, stacking=None):
     peak_gbs, peak_src, pipes = measured_peaks(lib, local)
     kern_s = kern_ms * 1e-3
     alg = algorithmic_bytes_per_quartet(ncols, subsample)
@@ -262,6 +283,8 @@ def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local
     rec = ncu_record(config, subsample)
     ntiles, chunks = info["ntiles"], info["row_words"] / 128.0
     products = ntiles if subsample else chunks               # 16 x 16 x 1024 tile products per quartet
+    if subsample and stacking and stacking["tile_products_per_quartet"] < (1 << 32) / max(1, quartets_per_launch) * 0.9:
+        products = stacking["tile_products_per_quartet"]     # stacked tiles: fewer products than tiles
     imma_per_quartet = 64.0 * products
     alu_per_quartet = 32.0 * (320.0 * products + (36.0 * chunks if subsample else 0.0))
     block = {
@@ -279,6 +302,8 @@ def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local
         "alu": {"frac": alu_per_quartet * quartets_per_launch / kern_s / (2.0 * pipes["lop3"]), "peak_per_s": 2.0 * pipes["lop3"],
                 "note": "LOP3/SHF thread-ops of the bit-plane unpack and of the per-locus selection against tq_microbench kind 1"},
     }
+    if stacking:
+        block["stacking"] = stacking
     binding = None
     if rec:
         binding = {k: rec.get(k) for k in ("issue_active_pct", "alu_pipe_pct", "fp64_pipe_pct", "lsu_pipe_pct",
@@ -286,8 +311,10 @@ def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local
                                             "source")}
         if rec.get("l2_to_sm_bytes_per_launch") and rec.get("l2_stream_peak_bytes_per_s"):
             binding["l2_to_sm_frac_of_stream_peak"] = rec["l2_to_sm_bytes_per_launch"] / kern_s / rec["l2_stream_peak_bytes_per_s"]
-        binding["note"] = ("ncu counters of the committed capture of this launch shape; no single pipe saturates: the kernel is "
-                           "bound by issue slots shared between the integer count warps and the FP64 score warps")
+        binding["tensor_pipe_pct"] = rec.get("tensor_pipe_pct")
+        binding["note"] = ("ncu counters of the committed capture of this launch shape.  The legacy IMMA and the ALU pipe (LOP3 / SHF "
+                           "of the bit-plane unpack and the per-locus selection) share an issue port: alu_pipe_pct + tensor_pipe_pct "
+                           "is the port's load and what binds the count warps")
     return block, binding
 
 
@@ -365,6 +392,8 @@ def bench_static(config, world, rank, local, dev, lib, steps, warmup, subsample=
                kernel=lib.tq_last_kernel().decode(),
                quartets_per_launch=hi - lo, launches=int(launches), ncols=int(tmparr.shape[1]), info=dict(eng.info),
                tmparr=tmparr, tmpmap=tmpmap, quartets=quartets)
+    if subsample:
+        res["stacking"] = stacking_stats(lib, eng, lambda: eng.resolve(qd[lo:hi], subsample), hi - lo)
     if e2e:
         # end to end through the reference-facing host API (pinned host buffers; plan + H2D + pack + resolve + D2H);
         # under N ranks every rank resolves its quartet range of the same matrix
@@ -442,6 +471,7 @@ def bench_replicates(config, world, rank, local, dev, lib, steps, warmup, sample
     kern_ms = statistics.mean(e["resolve_start"].elapsed_time(e["resolve_end"]) for e in ev)
     gather_ms = statistics.mean(e["resolve_end"].elapsed_time(e["gather_end"]) for e in ev)
     info = dict(preps[-1].engine.info)
+    stacking = stacking_stats(lib, preps[-1].engine, lambda: pipe.resolve(preps[-1]), -(-Q // world))
     # ---- e2e: the same loop by wall clock, host draws + H2D + D2H of the results on rank 0 inside ----------------
     barrier(world, dev)
     t0 = time.perf_counter()
@@ -455,7 +485,7 @@ def bench_replicates(config, world, rank, local, dev, lib, steps, warmup, sample
     d2h = Q * 32 + Q * 16                                                          # results + quartet ids, rank 0
     res = dict(Q=Q, value=Q * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps, kern_ms=kern_ms,
                quartets_per_launch=-(-Q // world), launches=int(launches), ncols=int(info["ncols"]), info=info,
-               clocks=clocks, wall=wall, kernel=lib.tq_last_kernel().decode(), sampler_name=sampler,
+               clocks=clocks, wall=wall, kernel=lib.tq_last_kernel().decode(), sampler_name=sampler, stacking=stacking,
                replicate={"prepare_ms": prepare_ms, "resolve_ms": kern_ms, "gather_ms": gather_ms,
                           "note": "device time of one rank's share of a replicate (CUDA events, rank 0): bootstrap column "
                                   "orders + planes of this rank's tip rows + all-gather + unranking | resolve of Q/N "
@@ -490,7 +520,7 @@ def run_ours(args):
     if world == 1 and args.config == DEFAULT_CONFIG and not args.quick:
         c2 = bench_static("C2", world, rank, local, dev, lib, 10, 3)
         roof, bind = roofline_block("C2", c2["ncols"], c2["quartets_per_launch"], c2["kern_ms"], c2["info"], lib, local,
-                                    kernel=c2["kernel"])
+                                    kernel=c2["kernel"], stacking=c2.get("stacking"))
         extra["c2"] = {"config": describe("C2"), "value": c2["value"], "ms_per_step": c2["ms_per_step"], "e2e": c2["e2e"],
                        "roofline": roof, "binding": bind,
                        "note": "BASELINE configs[1] (the 1-B200 shape): replicate 0 re-resolved against the resident matrix, "
@@ -509,7 +539,7 @@ def run_ours(args):
         return
 
     roofline, binding = roofline_block(args.config, res["ncols"], res["quartets_per_launch"], res["kern_ms"], res["info"],
-                                       lib, local, kernel=res["kernel"])
+                                       lib, local, kernel=res["kernel"], stacking=res.get("stacking"))
     cpu = None
     if world == 1 and not args.no_cpu:
         quartets = res.get("quartets")
