@@ -323,11 +323,12 @@ def pairgemm_tiles(quartets: np.ndarray, ntips: int) -> int:
     (the device planner's count, recomputed on the host for the roofline arithmetic; tq_pairgemm.cu)."""
     q = quartets.astype(np.int64)
     n = ntips
-    rp = q[:, 1] * (q[:, 1] - 1) // 2 + q[:, 0]
     cp = q[:, 2] * (2 * n - 1 - q[:, 2]) // 2 + q[:, 3] - q[:, 2] - 1
     npairs = n * (n - 1) // 2
     ntc = (npairs + 15) // 16
-    return int(len(np.unique((rp // 8) * ntc + cp // 16)))
+    # the planner counts the tiles under both row-pair numberings (lexicographic / by (t1, t0)) and takes the fewer
+    rows = (q[:, 0] * (2 * n - 1 - q[:, 0]) // 2 + q[:, 1] - q[:, 0] - 1, q[:, 1] * (q[:, 1] - 1) // 2 + q[:, 0])
+    return min(int(len(np.unique((rp // 8) * ntc + cp // 16))) for rp in rows)
 
 
 def tensor_block(quartets, ntips, padded_cols, kern_ms):

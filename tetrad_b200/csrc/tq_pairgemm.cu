@@ -36,6 +36,7 @@
 // other kernels'.  Applies when the list holds >= 30 % of all C(n,4) quartets (exhaustive lists in practice; a sparse
 // random sample would compute 128 candidates to use one or two -- the per-quartet kernel keeps those).
 #include "tq_kernels.cuh"
+#include <cstdlib>
 #include "tq_device.cuh"
 #include "tq_svd.cuh"
 
@@ -85,11 +86,18 @@ struct PairGemmArgs {
     const uint2 *entries;          // (quartet index, local row pair << 8 | local column pair), bucketed by cell
     uint32_t *counts;              // [m][256]
     const uint32_t *flags;         // flags[0] != 0: this chunk takes the GEMM route (else the kernels return at once)
+    const uint32_t *rowmode;       // rowmode[0]: numbering of the row pairs the planner chose for this chunk (kRowsLex / kRowsT1)
 };
 
-// Pair numbering, rows and columns alike: pairs (u < v) in lexicographic order, index = off(u) + v - u - 1.  A contiguous
-// range of a lexicographic quartet list (one rank's share, one chunk) is then a contiguous range of row pairs: its tiles
-// stay dense.
+// Pair numbering.  Column pairs (t2 < t3): lexicographic, index = off(t2) + t3 - t2 - 1.  Row pairs (t0 < t1): the planner
+// counts the non-empty tiles under TWO numberings and takes the one with fewer, per chunk, on the device:
+//   kRowsLex  lexicographic like the columns.  A contiguous range of a lexicographic quartet list (one rank's share, one
+//             chunk of a long list) is a contiguous range of row pairs, so its tiles stay dense; but a row block holds eight
+//             different t1, and every t2 among them gives half-empty tiles (C2, whole list: 2 879 tiles, 62 % wanted).
+//   kRowsT1   by (t1, t0): a row block shares its t1, so a tile is wanted (t1 < t2) as a whole (C2, whole list: 1 958
+//             tiles, 92 % wanted -- 16.7 instead of 20.9 ms); thin ranges of the list scatter over all row blocks (an
+//             eighth of the C2 list: 987 tiles against 300).
+static constexpr uint32_t kRowsLex = 0u, kRowsT1 = 1u;
 __host__ __device__ __forceinline__ uint32_t pair_offset(uint32_t u, uint32_t n) { return u * (2 * n - 1 - u) / 2; }
 __host__ __device__ __forceinline__ uint32_t pair_index(uint32_t u, uint32_t v, uint32_t n) { return pair_offset(u, n) + v - u - 1; }
 
@@ -106,10 +114,21 @@ __device__ __forceinline__ uint2 unrank_pair(uint32_t idx, uint32_t n)
 // ------------------------------------------------------------------------------------------
 // planner: bucket the quartets by tile
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool quartet_cell(uint4 t, uint32_t n, uint32_t ntc, uint32_t &cell, uint32_t &local)
+__device__ __forceinline__ uint2 unrank_rowpair_t1(uint32_t rp)
+{
+    uint32_t t1 = (uint32_t)((1.0 + sqrt(1.0 + 8.0 * (double)rp)) * 0.5);
+    while (t1 * (t1 - 1) / 2 > rp) --t1;
+    while (t1 * (t1 + 1) / 2 <= rp) ++t1;
+    return make_uint2(rp - t1 * (t1 - 1) / 2, t1);
+}
+__device__ __forceinline__ uint32_t rowpair_index(uint32_t t0, uint32_t t1, uint32_t n, uint32_t rowmode)
+{
+    return rowmode == kRowsT1 ? t1 * (t1 - 1) / 2 + t0 : pair_index(t0, t1, n);
+}
+__device__ __forceinline__ bool quartet_cell(uint4 t, uint32_t n, uint32_t ntc, uint32_t rowmode, uint32_t &cell, uint32_t &local)
 {
     if (!(t.x < t.y && t.y < t.z && t.z < t.w && t.w < n)) return false;      // out of range, or not ascending
-    const uint32_t rp = pair_index(t.x, t.y, n), cp = pair_index(t.z, t.w, n);
+    const uint32_t rp = rowpair_index(t.x, t.y, n, rowmode), cp = pair_index(t.z, t.w, n);
     cell = (rp / kRP) * ntc + cp / kCP;
     local = ((rp % kRP) << 8) | (cp % kCP);
     return true;
@@ -118,15 +137,42 @@ __device__ __forceinline__ bool quartet_cell(uint4 t, uint32_t n, uint32_t ntc, 
 // stats[0]: quartets with a tip out of range; stats[1]: quartets in range whose tips are not ascending (the GEMM needs
 // ascending tips; a chunk that holds one goes to the per-quartet kernel, which does not care)
 __global__ void __launch_bounds__(256) pg_count_kernel(const uint4 *__restrict__ quartets, int64_t m, uint32_t n, uint32_t ntc,
-                                                       uint32_t *__restrict__ cell_count, uint32_t *__restrict__ stats)
+                                                       uint32_t *__restrict__ cell_count, uint32_t *__restrict__ cell_count_t1,
+                                                       uint32_t *__restrict__ stats)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= m) return;
     const uint4 t = __ldg(quartets + q);
     uint32_t cell, local;
-    if (quartet_cell(t, n, ntc, cell, local)) atomicAdd(cell_count + cell, 1u);
-    else if (t.x >= n || t.y >= n || t.z >= n || t.w >= n) atomicAdd(stats, 1u);
+    if (quartet_cell(t, n, ntc, kRowsLex, cell, local)) {
+        atomicAdd(cell_count + cell, 1u);
+        quartet_cell(t, n, ntc, kRowsT1, cell, local);
+        atomicAdd(cell_count_t1 + cell, 1u);
+    } else if (t.x >= n || t.y >= n || t.z >= n || t.w >= n) atomicAdd(stats, 1u);
     else atomicAdd(stats + 1, 1u);
+}
+
+// nonempty[0 / 1] = non-empty cells (= tiles to compute) under the lexicographic / the (t1, t0) row numbering
+__global__ void __launch_bounds__(256) pg_nonempty_kernel(const uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_count_t1,
+                                                          uint32_t ncells, uint32_t *__restrict__ nonempty)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = __syncthreads_count(i < ncells && cell_count[i] != 0u);
+    const int b = __syncthreads_count(i < ncells && cell_count_t1[i] != 0u);
+    if (threadIdx.x == 0) {
+        if (a) atomicAdd(nonempty, (uint32_t)a);
+        if (b) atomicAdd(nonempty + 1, (uint32_t)b);
+    }
+}
+
+// The numbering with fewer tiles wins (ties: lexicographic); its counts become THE cell counts of the chunk.
+__global__ void __launch_bounds__(256) pg_pick_kernel(uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_count_t1,
+                                                      uint32_t ncells, const uint32_t *__restrict__ nonempty, uint32_t *__restrict__ rowmode)
+{
+    const uint32_t mode = nonempty[1] < nonempty[0] ? kRowsT1 : kRowsLex;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) rowmode[0] = mode;
+    if (mode == kRowsT1 && i < ncells) cell_count[i] = cell_count_t1[i];
 }
 
 // The chunk's route, decided where the planner's result lives.  flags[0] = 1: tip-pair GEMM + score kernel; 0: the
@@ -175,13 +221,13 @@ __global__ void __launch_bounds__(256) pg_compact_kernel(const uint32_t *__restr
 }
 
 __global__ void __launch_bounds__(256) pg_fill_kernel(const uint4 *__restrict__ quartets, int64_t m, uint32_t n, uint32_t ntc,
-                                                      const uint32_t *__restrict__ cell_off, uint32_t *__restrict__ cell_fill,
-                                                      uint2 *__restrict__ entries)
+                                                      const uint32_t *__restrict__ rowmode, const uint32_t *__restrict__ cell_off,
+                                                      uint32_t *__restrict__ cell_fill, uint2 *__restrict__ entries)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= m) return;
     uint32_t cell, local;
-    if (!quartet_cell(__ldg(quartets + q), n, ntc, cell, local)) return;
+    if (!quartet_cell(__ldg(quartets + q), n, ntc, rowmode[0], cell, local)) return;
     const uint32_t pos = cell_off[cell] + atomicAdd(cell_fill + cell, 1u);
     entries[pos] = make_uint2((uint32_t)q, local);
 }
@@ -259,7 +305,7 @@ pair_gemm_kernel(PairGemmArgs args)
     tcgen05_fence_after();
     const uint32_t tmem_base = sh.tmem_base;
 
-    const uint32_t tile_lo = 0u, tile_hi = args.ntiles[0];
+    const uint32_t tile_lo = 0u, tile_hi = args.ntiles[0], rowmode = args.rowmode[0];
     const uint32_t nst = args.row_u4 / kKW;                  // stages per tile (row_u4 is a multiple of 32)
     const uint32_t stage0 = smem_u32(stages);
 
@@ -274,7 +320,10 @@ pair_gemm_kernel(PairGemmArgs args)
             const uint32_t cell = __ldg(args.tile_list + tile);
             const uint32_t tr = cell / args.ntc, tc = cell % args.ntc;
             uint2 pr;                                        // my pair: (tip of the first plane, tip of the second plane)
-            if (is_a) { const uint32_t rp = tr * kRP + (r >> 4); pr = unrank_pair(rp < args.npairs ? rp : args.npairs - 1, args.ntips); }
+            if (is_a) {
+                const uint32_t rp = tr * kRP + (r >> 4), rq = rp < args.npairs ? rp : args.npairs - 1;
+                pr = rowmode == kRowsT1 ? unrank_rowpair_t1(rq) : unrank_pair(rq, args.ntips);
+            }
             else { const uint32_t cp = tc * kCP + (r >> 4); pr = unrank_pair(cp < args.npairs ? cp : args.npairs - 1, args.ntips); }
             const uint32_t *p0 = args.planes + (size_t)pr.x * args.row_u4 * 4 + ((r >> 2) & 3u);
             const uint32_t *p1 = args.planes + (size_t)pr.y * args.row_u4 * 4 + (r & 3u);
@@ -474,19 +523,20 @@ cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_plane
     cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)ncells + 1, stream);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const int64_t mcap = m < chunk_cap ? m : chunk_cap;
-    // scratch: cell_count | cell_off (+1) | flag | flag_scan (+1) | cell_fill | tile_list | small words | entries | counts | cub temp
+    // scratch: cell_count | cell_count_t1 | cell_off (+1) | flag | flag_scan (+1) | cell_fill | tile_list | small words | entries | counts | cub temp
     const size_t cb = up(((size_t)ncells + 1) * 4);
-    const size_t o_count = 0, o_off = o_count + cb, o_flag = o_off + cb, o_fscan = o_flag + cb, o_fill = o_fscan + cb,
-                 o_list = o_fill + cb, o_small = o_list + cb, o_entries = o_small + 256, o_counts = o_entries + up((size_t)mcap * 8),
+    const size_t o_count = 0, o_count2 = o_count + cb, o_off = o_count2 + cb, o_flag = o_off + cb, o_fscan = o_flag + cb,
+                 o_fill = o_fscan + cb, o_list = o_fill + cb, o_small = o_list + cb, o_entries = o_small + 256, o_counts = o_entries + up((size_t)mcap * 8),
                  o_temp = o_counts + (d_counts ? 0 : up((size_t)mcap * 1024)), total = o_temp + up(temp_bytes);
     char *scratch = nullptr;
     cudaError_t e = cudaMallocAsync(&scratch, total, stream);
     if (e != cudaSuccess) return e;
-    uint32_t *cell_count = (uint32_t *)(scratch + o_count), *cell_off = (uint32_t *)(scratch + o_off);
+    uint32_t *cell_count = (uint32_t *)(scratch + o_count), *cell_count_t1 = (uint32_t *)(scratch + o_count2);
+    uint32_t *cell_off = (uint32_t *)(scratch + o_off);
     uint32_t *flag = (uint32_t *)(scratch + o_flag), *fscan = (uint32_t *)(scratch + o_fscan);
     uint32_t *cell_fill = (uint32_t *)(scratch + o_fill), *tile_list = (uint32_t *)(scratch + o_list);
-    uint32_t *small = (uint32_t *)(scratch + o_small);          // [0] tiles, [1..2] stats, [4] route flag
-    uint32_t *ntiles = small, *stats = small + 1, *flags = small + 4;
+    uint32_t *small = (uint32_t *)(scratch + o_small);          // [0] tiles, [1..2] stats, [4] route flag, [5] row numbering, [6..7] tiles under either
+    uint32_t *ntiles = small, *stats = small + 1, *flags = small + 4, *rowmode = small + 5, *nonempty = small + 6;
     uint2 *entries = (uint2 *)(scratch + o_entries);
 
     for (int64_t c0 = 0; c0 < m; c0 += chunk_cap) {
@@ -494,22 +544,25 @@ cudaError_t launch_resolve_pairgemm(const PlanDev &plan, const uint32_t *d_plane
         uint32_t *counts = d_counts ? d_counts + (size_t)c0 * 256 : (uint32_t *)(scratch + o_counts);
         PG_CHECK(cudaMemsetAsync(scratch, 0, o_entries, stream));         // counts, offsets, flags, scans, fills, small words
         const unsigned qb = (unsigned)((mc + 255) / 256), cbk = (ncells + 1 + 255) / 256;
-        pg_count_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_count, stats);
+        pg_count_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_count, cell_count_t1, stats);
+        pg_nonempty_kernel<<<cbk, 256, 0, stream>>>(cell_count, cell_count_t1, ncells, nonempty);
+        pg_pick_kernel<<<cbk, 256, 0, stream>>>(cell_count, cell_count_t1, ncells, nonempty, rowmode);
         PG_CHECK(cub::DeviceScan::ExclusiveSum(scratch + o_temp, temp_bytes, cell_count, cell_off, (int)ncells + 1, stream));
         pg_flag_kernel<<<cbk, 256, 0, stream>>>(cell_count, ncells, flag);
         PG_CHECK(cub::DeviceScan::ExclusiveSum(scratch + o_temp, temp_bytes, flag, fscan, (int)ncells + 1, stream));
         pg_compact_kernel<<<cbk, 256, 0, stream>>>(cell_count, fscan, ncells, tile_list, ntiles);
         // cell_off[ncells] = number of bucketed quartets (the scan runs over ncells + 1 elements)
         pg_decide_kernel<<<1, 1, 0, stream>>>(ntiles, cell_off + ncells, stats, force, flags, route_dev);
-        pg_fill_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, cell_off, cell_fill, entries);
+        pg_fill_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, ntc, rowmode, cell_off, cell_fill, entries);
         pg_mark_bad_kernel<<<qb, 256, 0, stream>>>(quartets + c0, mc, n, flags, d_rscor + 3 * c0, rstat + c0, d_status);
-        g_launches += 9;
+        g_launches += 11;
         PG_CHECK(cudaGetLastError());
 
         PairGemmArgs args;
         args.planes = d_planes; args.row_u4 = plan.row_u4; args.ntips = n; args.npairs = np; args.ntc = ntc;
         args.tile_list = tile_list; args.ntiles = ntiles; args.cell_off = cell_off; args.cell_count = cell_count;
         args.entries = entries; args.counts = counts; args.flags = flags;
+        args.rowmode = rowmode;
         pair_gemm_kernel<<<num_sms, kGemmThreads, gemm_smem, stream>>>(args);
         score_counts_kernel<<<num_sms, kScoreWarps * 32, score_smem, stream>>>(counts, quartets + c0, entries, cell_off + ncells, flags,
                                                                              seed, d_rscor + 3 * c0, rstat + c0,
