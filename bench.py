@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--impl reference]
 
 Default workload: BASELINE config C4, the one `north_star` quotes its target on (200 tips, 200 000 loci, 1 M SNPs,
-1 M random quartets per replicate, bootstrap replicates; it fits one GPU: 422 MB packed).  One "step" = ONE BOOTSTRAP
+1 M random quartets per replicate, bootstrap replicates; it fits one GPU: 200 MB of seqarr, 105 MB packed).  One "step" = ONE BOOTSTRAP
 REPLICATE through the replicate loop the CLI runs (`tetrad_b200.replicate.ReplicatePipeline`, what
 `run_inference` drives): bootstrap planes packed on the device from the resident `seqarr` (every rank packs its share
 of the tip rows, planes all-gathered over NVLink), quartet ranks unranked on the device, this rank's contiguous
@@ -13,7 +13,8 @@ to rank 0 with NCCL.  STRONG scaling: a replicate has the same 1 M quartets what
 
 * `value`: Q * K / device time of K replicates (one CUDA-event pair around the whole pipelined region on the launching
   stream, max over ranks; barrier + synchronize on both sides).  The replicate's draws (bootstrap loci, quartet ranks)
-  are taken before the region starts and `seqarr` is resident; every replicate is a new 422 MB matrix (> L2).
+  are taken before the region starts and `seqarr` is resident; every replicate is a different draw packed from the
+  200 MB `seqarr` into a new 105 MB plane matrix (two engines alternate: > L2 together with the results).
 * `e2e`: the same loop through the same public API by wall clock, now with the host draws of every replicate, their
   host->device copies, and the device->host read of the replicate's results (and quartet ids) on rank 0 inside.
 * `--config C1|C2` (no bootstraps, exhaustive list): a step re-resolves replicate 0 against the resident matrix
@@ -552,8 +553,11 @@ def run_ours(args):
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{nq} random quartets of the replicate-0 quartet set in {dt:.1f} s, fork pool of {cores} workers, "
                          "OPENBLAS_NUM_THREADS=1", "port_vs_reference": port_calibration()}
-    setup = {"l2": "every replicate is a new packed matrix larger than L2" if replicate_mode else
-                   "flushed between steps (256 MiB write outside the per-step CUDA events)",
+    planes_mb = res["info"]["row_words"] * 4.0 * cfg["ntips"] / 1e6
+    seq_mb = cfg["ntips"] * float(res["info"]["ncols"]) / 1e6
+    setup = {"l2": (f"inputs larger than L2: every replicate is a different bootstrap draw, packed on the device from the resident "
+                    f"{seq_mb:.0f} MB seqarr into a new {planes_mb:.0f} MB plane matrix (two engines alternate, so two of them are live)")
+                   if replicate_mode else "flushed between steps (256 MiB write outside the per-step CUDA events)",
              "parallelism": f"quartet ranges x{world} (contiguous shard per rank), NCCL gather to rank 0" +
                             (", bootstrap planes packed by tip-row shares + NCCL all-gather" if replicate_mode and world > 1 else ""),
              "quartets_per_step": res["Q"]}
