@@ -553,11 +553,6 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
     if ((ncols > 0 && ntips > 0 && !h_tmparr) || (ncols > 0 && !h_locus))
         return fail(TQ_EINVAL, "tq_resolve_host: NULL input");
     if (m > 0 && (!h_quartets || !h_rscor || !h_rstat)) return fail(TQ_EINVAL, "tq_resolve_host: NULL quartets/outputs");
-    for (int64_t q = 0; q < m; ++q)
-        for (int i = 0; i < 4; ++i)
-            if ((int64_t)h_quartets[4 * q + i] >= ntips)
-                return fail(TQ_EINVAL, "tq_resolve_host: quartet %lld has tip index %u >= ntips %lld",
-                            (long long)q, h_quartets[4 * q + i], (long long)ntips);
     c->last_h2d = c->last_d2h = 0;
     if (m == 0) return TQ_OK;
     DeviceGuard guard(c->device);
@@ -618,8 +613,21 @@ int tq_resolve_host(tq_ctx *c, const uint8_t *h_tmparr, int64_t ntips, int64_t n
         if (h_counts) TQ_CUDA(cudaMemcpyAsync(h_counts + 256 * lo, o + o_counts + lo * 1024, (size_t)n * 1024, cudaMemcpyDeviceToHost, c->copy_stream));
     }
     c->last_d2h += m * 32 + (h_minrank ? m * 4 : 0) + (h_counts ? m * 1024 : 0);
+    // The tip indices are checked on the host WHILE the device works (the kernels flag an index out of range themselves
+    // and touch nothing outside the matrix, so launching first is safe); the error, if any, is reported after the queue
+    // has drained, and the outputs of a failed call mean nothing.
+    int64_t bad_q = -1;
+    for (int64_t q = 0; q < m && bad_q < 0; ++q)
+        for (int i = 0; i < 4; ++i)
+            if ((int64_t)h_quartets[4 * q + i] >= ntips) { bad_q = q; break; }
     TQ_CUDA(cudaStreamSynchronize(c->copy_stream));
     TQ_CUDA(cudaStreamSynchronize(c->stream));
+    if (bad_q >= 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 4; ++i)
+            if ((int64_t)h_quartets[4 * bad_q + i] >= ntips) { t = h_quartets[4 * bad_q + i]; break; }
+        return fail(TQ_EINVAL, "tq_resolve_host: quartet %lld has tip index %u >= ntips %lld", (long long)bad_q, t, (long long)ntips);
+    }
     return TQ_OK;
 }
 
