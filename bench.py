@@ -315,7 +315,9 @@ def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local
         binding["tensor_pipe_pct"] = rec.get("tensor_pipe_pct")
         binding["note"] = ("ncu counters of the committed capture of this launch shape.  The legacy IMMA and the ALU pipe (LOP3 / SHF "
                            "of the bit-plane unpack and the per-locus selection) share an issue port: alu_pipe_pct + tensor_pipe_pct "
-                           "is the port's load and what binds the count warps")
+                           "is the port's load.  issue_active_pct includes the mbarrier poll loops of idle score warps (a fifth of "
+                           "the executed instructions at C4, harmless for the run time: profiles/r02_warp_mix.md section 7); "
+                           "the count warps are bound by the latency of their own dependent instruction streams")
     return block, binding
 
 
