@@ -287,7 +287,7 @@ def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local
     if subsample and stacking and stacking["tile_products_per_quartet"] < (1 << 32) / max(1, quartets_per_launch) * 0.9:
         products = stacking["tile_products_per_quartet"]     # stacked tiles: fewer products than tiles
     imma_per_quartet = 64.0 * products
-    alu_per_quartet = 32.0 * (320.0 * products + (36.0 * chunks if subsample else 0.0))
+    alu_per_quartet = 32.0 * (320.0 * products + (24.0 * chunks if subsample else 0.0))   # stage 1 on code planes: 18 LOP3 + loop arithmetic
     block = {
         "bound": "hbm", "kernel": kernel or lib.tq_last_kernel().decode(), "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": rec.get("dram_bytes_per_launch") if rec else None, "peak_source": peak_src,

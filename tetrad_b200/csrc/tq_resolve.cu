@@ -521,7 +521,7 @@ __device__ __forceinline__ void merge_tile_planes(const uint32_t (&MA)[4], const
 }
 
 // Count the selected loci in `ovf` (bit slots already taken in P) one by one: pattern index ((a*4+b)*4+c)*4+d from the
-// one-hot planes (A, C, G, T = 0..3: low bit = C | T, high bit = G | T), one shared-memory atomic each.
+// tile's merged code planes (A, C, G, T = 0..3: H = high bit, L = low bit, one word per tip), one shared-memory atomic each.
 // The kernel is bound by the port the ALU pipe shares with the legacy IMMA (LOP3 / SHF / IMMA of the other count warps),
 // while the FMA pipe idles: the eight code bits of a locus are therefore pulled out with integer MULTIPLIES -- w * 2^(31-pos)
 // puts bit `pos` on top, mul.hi by 2 brings it down to 0/1, mad.lo chains them -- and `two` is a kernel argument so that ptxas
@@ -544,11 +544,10 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
-__device__ __forceinline__ void scatter_overflow(uint32_t ovf, const uint32_t (&MA)[4], const uint32_t (&MB)[4],
-                                                 const uint32_t (&MC)[4], const uint32_t (&MD)[4], uint32_t *T, uint32_t two)
+__device__ __forceinline__ void scatter_overflow(uint32_t ovf, const uint32_t (&H)[4], const uint32_t (&L)[4], uint32_t *T,
+                                                 uint32_t two)
 {
-    const uint32_t la = MA[1] | MA[3], ha = MA[2] | MA[3], lb = MB[1] | MB[3], hb = MB[2] | MB[3];
-    const uint32_t lc = MC[1] | MC[3], hc = MC[2] | MC[3], ld = MD[1] | MD[3], hd = MD[2] | MD[3];
+    const uint32_t ha = H[0], la = L[0], hb = H[1], lb = L[1], hc = H[2], lc = L[2], hd = H[3], ld = L[3];
     const uint32_t four = mul_lo(two, two), sixteen = mul_lo(four, four);
     // two loci per trip (the highest and the lowest set bit): half the trips of the lane with the most overflow
     while (ovf) {
@@ -599,28 +598,34 @@ __device__ __forceinline__ void flush_mma(int (&acc)[kScales][2][4], uint32_t *T
         }
 }
 
-// One rank chunk of stage 1 (subsample mode): sel = complete & segregating & ~taken; a selected column is complete, so
-// the T plane of every tip is what the other three leave of `taken`: three merged planes per tip are updated per chunk,
-// the fourth is derived once per tile (finish_tile_planes).
-__device__ __forceinline__ void select_chunk(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, uint32_t &taken,
-                                             uint32_t (&MA)[4], uint32_t (&MB)[4], uint32_t (&MC)[4], uint32_t (&MD)[4])
+// ---- subsample mode on CODE planes --------------------------------------------------------------------------------
+// The packed matrix is one-hot ({A, C, G, T} words: what full mode, the tip-pair GEMM and the POPC kernel want).  For the
+// per-locus selection a 2-bit code per base plus a validity bit is cheaper: launch_resolve_mma<true> first converts the
+// matrix into {hi, lo, valid, 0} words (A, C, G, T = 0..3: hi = G | T, lo = C | T; one streaming pass, 0.1 ms at C4, into
+// stream-ordered scratch), and the rank-chunk loop then needs 17 LOP3 instead of 30: complete = AND of four validity words
+// (2), some tip differs from the first = (a^b)|(a^c)|(a^d) on the hi and on the lo words (4), sel (2), taken (1), eight
+// merged code planes (8).  The sixteen one-hot planes the tile product wants are expanded once per tile.
+__global__ void __launch_bounds__(256) planes_to_codes_kernel(const uint4 *__restrict__ planes, uint4 *__restrict__ codes, size_t n)
 {
-    const uint32_t valid = (a.x | a.y | a.z | a.w) & (b.x | b.y | b.z | b.w) &
-                           (c.x | c.y | c.z | c.w) & (d.x | d.y | d.z | d.w);
-    const uint32_t same = (a.x & b.x & c.x & d.x) | (a.y & b.y & c.y & d.y) |
-                          (a.z & b.z & c.z & d.z) | (a.w & b.w & c.w & d.w);
-    const uint32_t sel = valid & ~same & ~taken;
-    taken |= sel;
-    MA[0] |= a.x & sel; MA[1] |= a.y & sel; MA[2] |= a.z & sel;
-    MB[0] |= b.x & sel; MB[1] |= b.y & sel; MB[2] |= b.z & sel;
-    MC[0] |= c.x & sel; MC[1] |= c.y & sel; MC[2] |= c.z & sel;
-    MD[0] |= d.x & sel; MD[1] |= d.y & sel; MD[2] |= d.z & sel;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 p = __ldg(planes + i);
+        codes[i] = make_uint4(p.z | p.w, p.y | p.w, p.x | p.y | p.z | p.w, 0u);
+    }
 }
-__device__ __forceinline__ void finish_tile_planes(uint32_t taken, uint32_t (&MA)[4], uint32_t (&MB)[4], uint32_t (&MC)[4],
-                                                   uint32_t (&MD)[4])
+// a.x = hi, a.y = lo, a.z = valid of 32 columns of the first tip, ...
+__device__ __forceinline__ void select_chunk_codes(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, uint32_t &taken,
+                                                   uint32_t (&H)[4], uint32_t (&L)[4])
 {
-    MA[3] = taken & ~(MA[0] | MA[1] | MA[2]); MB[3] = taken & ~(MB[0] | MB[1] | MB[2]);
-    MC[3] = taken & ~(MC[0] | MC[1] | MC[2]); MD[3] = taken & ~(MD[0] | MD[1] | MD[2]);
+    const uint32_t valid = a.z & b.z & c.z & d.z;
+    const uint32_t dh = (a.x ^ b.x) | (a.x ^ c.x) | (a.x ^ d.x), dl = (a.y ^ b.y) | (a.y ^ c.y) | (a.y ^ d.y);
+    const uint32_t sel = valid & ~taken & (dh | dl);
+    taken |= sel;
+    H[0] |= a.x & sel; H[1] |= b.x & sel; H[2] |= c.x & sel; H[3] |= d.x & sel;
+    L[0] |= a.y & sel; L[1] |= b.y & sel; L[2] |= c.y & sel; L[3] |= d.y & sel;
+}
+__device__ __forceinline__ void expand_tile_planes(uint32_t taken, uint32_t h, uint32_t l, uint32_t (&M)[4])
+{
+    M[0] = taken & ~h & ~l; M[1] = taken & ~h & l; M[2] = taken & h & ~l; M[3] = taken & h & l;
 }
 
 // Per-warp ring: stage 1 by cp.async (L1-bypassing .cg: consecutive quartets' shared rows hitting in L1 was measured 3 %
@@ -673,8 +678,7 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
         const uint32_t K = last ? 0u : Knext;
         if (tile + 1 < ntiles) Knext = __ldg(plan.tile_k + tile + 1);
         uint32_t taken = 0u;
-        uint32_t MA[4] = {0u, 0u, 0u, 0u}, MB[4] = {0u, 0u, 0u, 0u};
-        uint32_t MC[4] = {0u, 0u, 0u, 0u}, MD[4] = {0u, 0u, 0u, 0u};
+        uint32_t H[4] = {0u, 0u, 0u, 0u}, L[4] = {0u, 0u, 0u, 0u};      // subsample mode: merged code planes of the four tips
         for (uint32_t k = 0; k < K; ++k, ++u) {
             cp_async_wait<kMStages - 2>();            // chunk u has landed (chunks u+1 .. u+kMStages-2 may be in flight)
             const uint4 *st = ring + (u & (kMStages - 1)) * (4 * 32) + lane;
@@ -685,7 +689,7 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
                 cp_async_commit();
             }
             if (kSubsample) {
-                select_chunk(a, b, c, d, taken, MA, MB, MC, MD);
+                select_chunk_codes(a, b, c, d, taken, H, L);
             } else {
                 // full mode (resolve_quartets.py:92-95): every complete column counts; the four
                 // invariant patterns aaaa are zeroed by the caller
@@ -696,7 +700,9 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
             }
         }
         if (kSubsample) {
-            finish_tile_planes(taken, MA, MB, MC, MD);
+            uint32_t MA[4], MB[4], MC[4], MD[4];
+            expand_tile_planes(taken, H[0], L[0], MA); expand_tile_planes(taken, H[1], L[1], MB);
+            expand_tile_planes(taken, H[2], L[2], MC); expand_tile_planes(taken, H[3], L[3], MD);
             // The price of stacking this tile on the ones in P is known exactly: the lane with the most taken slots walks
             // its overflow bit by bit.  Past `stack_ovf` loci, or once `stack_fill` slots are in use, the stack is
             // multiplied out first and the tile starts a new one.
@@ -719,7 +725,7 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
                 occ |= taken;
                 ++n_stacked;
                 n_walk += worst;
-                if (worst) scatter_overflow(ovf, MA, MB, MC, MD, T, two);
+                if (worst) scatter_overflow(ovf, H, L, T, two);
             }
         }
     }
@@ -891,12 +897,26 @@ static cudaError_t launch_resolve_mma_mix(const PlanDev &plan, const uint4 *plan
     const unsigned grid = (unsigned)(want < num_sms ? want : num_sms);
     const int64_t fv = g_mma_flush.load();
     const uint32_t flush_every = (fv >= 1 && fv < (int64_t)kMmaFlushEvery) ? (uint32_t)fv : kMmaFlushEvery;
+    uint4 *codes = nullptr;
+    if (kSubsample) {                                // one-hot planes -> {hi, lo, valid, 0} words (see select_chunk_codes)
+        const size_t n = (size_t)ntips * plan.row_u4;
+        if (n) {
+            e = cudaMallocAsync(&codes, n * sizeof(uint4), stream);
+            if (e != cudaSuccess) return e;
+            const size_t blocks = (n + 255) / 256, cap = (size_t)num_sms * 16;
+            planes_to_codes_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(planes, codes, n);
+            ++g_launches;
+            planes = codes;
+        }
+    }
     kern<<<grid, kMmaWarps * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank,
                                                  d_status, flush_every, stack_fill_slots(), (uint32_t)g_stack_ovf.load(), 2u, d_skip);
     ++g_launches;
     g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
     g_last_count_warps = NC;
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (codes) cudaFreeAsync(codes, stream);
+    return e;
 }
 
 template <bool kSubsample>
