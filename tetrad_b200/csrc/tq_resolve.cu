@@ -499,27 +499,14 @@ __device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const ui
 
 // ---- stacking sparse tiles (subsample mode) ------------------------------------------------------------------------
 // A tile product costs the same whether 1 024 or 100 of the tile's loci selected a column, and on real and synthetic
-// data most loci select none for a given quartet (a column must be complete in all four tips and segregating: ~36 % of the
-// loci at the BASELINE shapes).  Bit positions carry no meaning once the planes are merged, so the merged planes of
-// SEVERAL tiles are stacked in P before one product is taken: a selected locus whose bit slot is still free (`put`) is
-// OR-ed into P; one whose slot is taken (`ovf`) is counted on the spot by a shared-memory atomic on its pattern index.
-// The product runs when the slots filled reach `stack_fill` (a warp-wide popcount per tile decides), so dense data
-// behaves as before (one product per tile, no overflow) and sparse data takes a fraction of the products.  Every selected
-// column is counted exactly once, by the product or by the atomic: the counts stay bit-exact.
-__device__ __forceinline__ void merge_tile_planes(const uint32_t (&MA)[4], const uint32_t (&MB)[4],
-                                                  const uint32_t (&MC)[4], const uint32_t (&MD)[4], uint32_t put,
-                                                  const MmaLanePtrs &lp)
-{
-    __syncwarp();                                    // the previous tile product's reads are over
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        lp.st[(0 + k) * kPStride] |= MA[k] & put;
-        lp.st[(4 + k) * kPStride] |= MB[k] & put;
-        lp.st[(8 + k) * kPStride] |= MC[k] & put;
-        lp.st[(12 + k) * kPStride] |= MD[k] & put;
-    }
-}
-
+// data most loci select none for a given quartet (a column must be complete in all four tips and segregating: 24 - 34 % of
+// the loci at the BASELINE shapes).  Bit positions carry no meaning once the planes are merged, so the merged code planes
+// of SEVERAL tiles are stacked -- in registers -- before one product is taken: a selected locus whose bit slot is still free
+// (`put`) is OR-ed into the stack; one whose slot is taken (`ovf`) is counted on the spot by a shared-memory atomic on its
+// pattern index.  The price of stacking a tile is known before it is paid (the busiest lane's number of such loci), so
+// dense data behaves as before (one product per tile, no overflow) and sparse data takes a fraction of the products.
+// Every selected column is counted exactly once, by the product or by the atomic: the counts stay bit-exact.
+//
 // Count the selected loci in `ovf` (bit slots already taken in P) one by one: pattern index ((a*4+b)*4+c)*4+d from the
 // tile's merged code planes (A, C, G, T = 0..3: H = high bit, L = low bit, one word per tip), one shared-memory atomic each.
 // The kernel is bound by the port the ALU pipe shares with the legacy IMMA (LOP3 / SHF / IMMA of the other count warps),
@@ -667,8 +654,9 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
     uint32_t u = 0;                                   // rank-chunk index along the rows
     const int ntiles = plan.ntiles;
     uint32_t Knext = ntiles > 0 ? __ldg(plan.tile_k) : 0u;
-    uint32_t occ = 0u;                                // bit slots of P in use (subsample mode: stacked tiles)
-    bool stacked = false;                             // P holds planes that no product has taken yet (warp-uniform)
+    uint32_t occ = 0u;                                // bit slots in use (subsample mode: stacked tiles)
+    uint32_t SH[4] = {0u, 0u, 0u, 0u}, SL[4] = {0u, 0u, 0u, 0u};   // the stack: merged code planes of the tiles not multiplied out yet
+    bool stacked = false;                             // the stack holds tiles that no product has taken yet (warp-uniform)
     uint32_t n_products = 0u, n_stacked = 0u, n_walk = 0u;   // diagnostics: status[1..3]
     // Subsample mode runs one extra, empty pass of the tile loop so that the product of the last stacked tiles is taken at
     // the same (single) call site as every other product: the IMMA body is in the instruction stream once.
@@ -700,16 +688,18 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
             }
         }
         if (kSubsample) {
-            uint32_t MA[4], MB[4], MC[4], MD[4];
-            expand_tile_planes(taken, H[0], L[0], MA); expand_tile_planes(taken, H[1], L[1], MB);
-            expand_tile_planes(taken, H[2], L[2], MC); expand_tile_planes(taken, H[3], L[3], MD);
-            // The price of stacking this tile on the ones in P is known exactly: the lane with the most taken slots walks
-            // its overflow bit by bit.  Past `stack_ovf` loci, or once `stack_fill` slots are in use, the stack is
-            // multiplied out first and the tile starts a new one.
+            // The stack of tiles lives in REGISTERS as eight code planes (SH, SL) + `occ`; stacking a tile is nine LOP3.  The
+            // price of stacking this tile is known exactly: the lane with the most taken slots walks its overflow bit by
+            // bit.  Past `stack_ovf` loci, or once `stack_fill` slots are in use, the stack is multiplied out first -- only
+            // then are its sixteen one-hot planes expanded and stored to the tile copy P -- and the tile starts a new one.
             const uint32_t ovf = taken & occ;
             const uint32_t worst = __reduce_max_sync(kFull, (uint32_t)__popc(ovf));
             const uint32_t filled = __reduce_add_sync(kFull, (uint32_t)__popc(occ));
             if (stacked && (last || worst > stack_ovf || filled >= stack_fill)) {
+                uint32_t MA[4], MB[4], MC[4], MD[4];
+                expand_tile_planes(occ, SH[0], SL[0], MA); expand_tile_planes(occ, SH[1], SL[1], MB);
+                expand_tile_planes(occ, SH[2], SL[2], MC); expand_tile_planes(occ, SH[3], SL[3], MD);
+                store_tile_planes(MA, MB, MC, MD, lp);
                 tile_product_mma(lp, acc);
                 ++n_products;
                 stacked = false;
@@ -717,11 +707,14 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
             }
             if (last) break;
             if (!stacked) {
-                store_tile_planes(MA, MB, MC, MD, lp);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { SH[i] = H[i]; SL[i] = L[i]; }
                 occ = taken;
                 stacked = true;
             } else {
-                merge_tile_planes(MA, MB, MC, MD, taken & ~occ, lp);
+                const uint32_t put = taken & ~occ;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { SH[i] |= H[i] & put; SL[i] |= L[i] & put; }
                 occ |= taken;
                 ++n_stacked;
                 n_walk += worst;
