@@ -639,8 +639,10 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
     const uint4 *g0 = planes + (size_t)tips.x * plan.row_u4 + lane, *g1 = planes + (size_t)tips.y * plan.row_u4 + lane;
     const uint4 *g2 = planes + (size_t)tips.z * plan.row_u4 + lane, *g3 = planes + (size_t)tips.w * plan.row_u4 + lane;
     const uint32_t ring_s = smem_u32(ring + lane);
-    auto issue = [&](uint32_t chunk) {
-        const uint32_t s = ring_s + (chunk & (kMStages - 1)) * (4 * 32 * 16), off = chunk * kTileWords;
+    constexpr uint32_t kStageBytes = 4 * 32 * 16, kRingMask = (kMStages - 1) * kStageBytes;
+    // chunk at uint4 offset `off` of the rows -> ring stage at byte offset `sb`
+    auto issue = [&](uint32_t sb, uint32_t off) {
+        const uint32_t s = ring_s + sb;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g0 + off) : "memory");
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s + 512), "l"(g1 + off) : "memory");
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s + 1024), "l"(g2 + off) : "memory");
@@ -648,10 +650,13 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
     };
 #pragma unroll
     for (int s = 0; s < kMStages - 1; ++s) {
-        if ((uint32_t)s < nchunks) issue(s);
+        if ((uint32_t)s < nchunks) issue(s * kStageBytes, s * kTileWords);
         cp_async_commit();
     }
-    uint32_t u = 0;                                   // rank-chunk index along the rows
+    // The loop's bookkeeping is two running values: the ring stage of the chunk being read (byte offset `rd`; the stage to
+    // refill is the one before it) and the row offset of the chunk to fetch (`gnext`, uint4 units).
+    uint32_t rd = 0u, gnext = (kMStages - 1) * kTileWords;
+    const uint32_t gend = nchunks * kTileWords;
     const int ntiles = plan.ntiles;
     uint32_t Knext = ntiles > 0 ? __ldg(plan.tile_k) : 0u;
     uint32_t occ = 0u;                                // bit slots in use (subsample mode: stacked tiles)
@@ -667,15 +672,15 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
         if (tile + 1 < ntiles) Knext = __ldg(plan.tile_k + tile + 1);
         uint32_t taken = 0u;
         uint32_t H[4] = {0u, 0u, 0u, 0u}, L[4] = {0u, 0u, 0u, 0u};      // subsample mode: merged code planes of the four tips
-        for (uint32_t k = 0; k < K; ++k, ++u) {
-            cp_async_wait<kMStages - 2>();            // chunk u has landed (chunks u+1 .. u+kMStages-2 may be in flight)
-            const uint4 *st = ring + (u & (kMStages - 1)) * (4 * 32) + lane;
+        for (uint32_t k = K; k != 0u; --k) {
+            cp_async_wait<kMStages - 2>();            // this chunk has landed (the next kMStages-2 may be in flight)
+            const uint4 *st = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(ring + lane) + rd);
             const uint4 a = st[0], b = st[32], c = st[64], d = st[96];
-            {   // refill the stage read in the previous iteration; keeps kMStages-1 chunks in flight
-                const uint32_t nu = u + kMStages - 1;
-                if (nu < nchunks) issue(nu);
-                cp_async_commit();
-            }
+            // refill the stage read in the previous iteration; keeps kMStages-1 chunks in flight
+            if (gnext < gend) issue((rd + kRingMask) & kRingMask, gnext);
+            cp_async_commit();
+            gnext += kTileWords;
+            rd = (rd + kStageBytes) & kRingMask;
             if (kSubsample) {
                 select_chunk_codes(a, b, c, d, taken, H, L);
             } else {
