@@ -235,8 +235,8 @@ int tq_pairgemm_stats(int64_t out[2]);
  *   "mma_flush_every"  > 0: tile products between accumulator flushes of the tensor-core kernel
  *                      (default 16384; tests lower it to reach the flush path), 0 = default
  *   "stack_fill"       subsample mode stacks the merged planes of consecutive sparse tiles in one tile copy and takes ONE
- *                      tile product when this percentage of its 1024 bit slots is filled: -1 = default (85),
- *                      0 = one product per tile (never stack), 1..100
+ *                      tile product when this percentage of its 1024 bit slots is filled: -1 = default (100: the
+ *                      overflow rule "stack_ovf" alone decides), 0 = one product per tile (never stack), 1..99
  *   "stack_ovf"        a tile is stacked on the previous ones only if no lane has more than this many selected loci
  *                      whose bit slot is already taken (those are counted one by one, by shared-memory atomics);
  *                      otherwise the stack is multiplied out first.  0..32, default 7

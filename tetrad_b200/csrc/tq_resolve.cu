@@ -80,7 +80,7 @@ std::atomic<int> g_stack_stats{0};                       // != 0: the kernel add
 std::atomic<int> g_count_warps{initial_count_warps()};
 
 // Bit slots of P that must be filled before the stacked tiles' product is taken (count_quartet_mma).
-static constexpr int kStackFillPercent = 85;
+static constexpr int kStackFillPercent = 100;
 static uint32_t stack_fill_slots()
 {
     const int pct = g_stack_fill.load();
@@ -509,54 +509,31 @@ __device__ __forceinline__ void count_tile_mma(const uint32_t (&MA)[4], const ui
 //
 // Count the selected loci in `ovf` (bit slots already taken in P) one by one: pattern index ((a*4+b)*4+c)*4+d from the
 // tile's merged code planes (A, C, G, T = 0..3: H = high bit, L = low bit, one word per tip), one shared-memory atomic each.
-// The kernel is bound by the port the ALU pipe shares with the legacy IMMA (LOP3 / SHF / IMMA of the other count warps),
-// while the FMA pipe idles: the eight code bits of a locus are therefore pulled out with integer MULTIPLIES -- w * 2^(31-pos)
-// puts bit `pos` on top, mul.hi by 2 brings it down to 0/1, mad.lo chains them -- and `two` is a kernel argument so that ptxas
-// cannot turn the multiplies back into ALU-pipe shifts.
-__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b)
+// The count warps pay for every instruction of their own streams, so the eight code bits of a locus are gathered with two
+// instructions each: the plane word shifted right by the locus' position, then one funnel shift that pushes its lowest bit
+// into the top of the index under construction (first plane pushed ends up lowest).  Two loci per trip -- the highest and
+// the lowest set bit -- halve the trips of the lane with the most overflow.
+__device__ __forceinline__ uint32_t code_index(uint32_t pos, uint32_t ha, uint32_t la, uint32_t hb, uint32_t lb,
+                                               uint32_t hc, uint32_t lc, uint32_t hd, uint32_t ld)
 {
-    uint32_t r;
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
+    uint32_t idx = 0u;                               // ((a*4+b)*4+c)*4+d: ld is bit 0, ha bit 7
+    idx = __funnelshift_r(idx, ld >> pos, 1); idx = __funnelshift_r(idx, hd >> pos, 1);
+    idx = __funnelshift_r(idx, lc >> pos, 1); idx = __funnelshift_r(idx, hc >> pos, 1);
+    idx = __funnelshift_r(idx, lb >> pos, 1); idx = __funnelshift_r(idx, hb >> pos, 1);
+    idx = __funnelshift_r(idx, la >> pos, 1); idx = __funnelshift_r(idx, ha >> pos, 1);
+    return idx >> 24;
 }
-__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b)
-{
-    uint32_t r;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-}
-__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
-__device__ __forceinline__ void scatter_overflow(uint32_t ovf, const uint32_t (&H)[4], const uint32_t (&L)[4], uint32_t *T,
-                                                 uint32_t two)
+__device__ __forceinline__ void scatter_overflow(uint32_t ovf, const uint32_t (&H)[4], const uint32_t (&L)[4], uint32_t *T)
 {
     const uint32_t ha = H[0], la = L[0], hb = H[1], lb = L[1], hc = H[2], lc = L[2], hd = H[3], ld = L[3];
-    const uint32_t four = mul_lo(two, two), sixteen = mul_lo(four, four);
-    // two loci per trip (the highest and the lowest set bit): half the trips of the lane with the most overflow
     while (ovf) {
         const uint32_t pos = 31u - __clz(ovf);
         ovf ^= 1u << pos;
         const bool second = ovf != 0u;
         const uint32_t pos2 = second ? (uint32_t)__ffs(ovf) - 1u : pos;
         ovf &= ovf - 1u;
-        const uint32_t up = 0x80000000u >> pos, up2 = 0x80000000u >> pos2;      // 2^(31 - pos)
-        // bit `pos` of every code plane as 0 / 1, on the FMA pipe
-        const uint32_t b7 = mul_hi(mul_lo(ha, up), two), b6 = mul_hi(mul_lo(la, up), two);
-        const uint32_t b5 = mul_hi(mul_lo(hb, up), two), b4 = mul_hi(mul_lo(lb, up), two);
-        const uint32_t b3 = mul_hi(mul_lo(hc, up), two), b2 = mul_hi(mul_lo(lc, up), two);
-        const uint32_t b1 = mul_hi(mul_lo(hd, up), two), b0 = mul_hi(mul_lo(ld, up), two);
-        const uint32_t c7 = mul_hi(mul_lo(ha, up2), two), c6 = mul_hi(mul_lo(la, up2), two);
-        const uint32_t c5 = mul_hi(mul_lo(hb, up2), two), c4 = mul_hi(mul_lo(lb, up2), two);
-        const uint32_t c3 = mul_hi(mul_lo(hc, up2), two), c2 = mul_hi(mul_lo(lc, up2), two);
-        const uint32_t c1 = mul_hi(mul_lo(hd, up2), two), c0 = mul_hi(mul_lo(ld, up2), two);
-        const uint32_t idx = mad_lo(mad_lo(mad_lo(b7, two, b6), four, mad_lo(b5, two, b4)), sixteen,
-                                    mad_lo(mad_lo(b3, two, b2), four, mad_lo(b1, two, b0)));
-        const uint32_t idx2 = mad_lo(mad_lo(mad_lo(c7, two, c6), four, mad_lo(c5, two, c4)), sixteen,
-                                     mad_lo(mad_lo(c3, two, c2), four, mad_lo(c1, two, c0)));
+        const uint32_t idx = code_index(pos, ha, la, hb, lb, hc, lc, hd, ld);
+        const uint32_t idx2 = code_index(pos2, ha, la, hb, lb, hc, lc, hd, ld);
         atomicAdd(T + idx, 1u);
         if (second) atomicAdd(T + idx2, 1u);
     }
@@ -622,7 +599,7 @@ __device__ __forceinline__ void expand_tile_planes(uint32_t taken, uint32_t h, u
 template <bool kSubsample>
 __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uint4 *__restrict__ planes,
                                                   uint4 tips, const uint4 *ring, uint32_t *P, uint32_t *T, int lane,
-                                                  uint32_t flush_every, uint32_t stack_fill, uint32_t stack_ovf, uint32_t two, uint32_t *stats)
+                                                  uint32_t flush_every, uint32_t stack_fill, uint32_t stack_ovf, uint32_t *stats)
 {
     stack_fill &= 0x7FFFFFFFu;                        // the top bit asked for the diagnostics (`stats` is then non-null)
     static_assert((kMStages & (kMStages - 1)) == 0, "ring depth must be a power of two");
@@ -699,7 +676,8 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
             // then are its sixteen one-hot planes expanded and stored to the tile copy P -- and the tile starts a new one.
             const uint32_t ovf = taken & occ;
             const uint32_t worst = __reduce_max_sync(kFull, (uint32_t)__popc(ovf));
-            const uint32_t filled = __reduce_add_sync(kFull, (uint32_t)__popc(occ));
+            // (the fill rule is off by default -- 100 % -- and then costs nothing: the overflow rule alone decides)
+            const uint32_t filled = stack_fill < (uint32_t)kTileLoci ? __reduce_add_sync(kFull, (uint32_t)__popc(occ)) : 0u;
             if (stacked && (last || worst > stack_ovf || filled >= stack_fill)) {
                 uint32_t MA[4], MB[4], MC[4], MD[4];
                 expand_tile_planes(occ, SH[0], SL[0], MA); expand_tile_planes(occ, SH[1], SL[1], MB);
@@ -723,7 +701,7 @@ __device__ __forceinline__ void count_quartet_mma(const PlanDev &plan, const uin
                 occ |= taken;
                 ++n_stacked;
                 n_walk += worst;
-                if (worst) scatter_overflow(ovf, H, L, T, two);
+                if (worst) scatter_overflow(ovf, H, L, T);
             }
         }
     }
@@ -763,7 +741,7 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
                    const uint4 *__restrict__ quartets, int64_t m, uint64_t seed,
                    double *__restrict__ rscor, uint2 *__restrict__ rstat,
                    uint32_t *__restrict__ counts, uint32_t *__restrict__ minrank_out,
-                   uint32_t *__restrict__ status, uint32_t flush_every, uint32_t stack_fill, uint32_t stack_ovf, uint32_t two,
+                   uint32_t *__restrict__ status, uint32_t flush_every, uint32_t stack_fill, uint32_t stack_ovf,
                    const uint32_t *__restrict__ skip)
 {
     if (skip && skip[0]) return;                     // full mode: the tip-pair GEMM took this chunk (tq_pairgemm.cu)
@@ -809,7 +787,7 @@ resolve_mma_kernel(PlanDev plan, const uint4 *__restrict__ planes, uint32_t ntip
 #pragma unroll
             for (int i = 0; i < 8; ++i) T[lane + 32 * i] = 0u;
             __syncwarp();
-            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every, stack_fill, stack_ovf, two, (stack_fill & 0x80000000u) ? status : nullptr);
+            if (!bad) count_quartet_mma<kSubsample>(plan, planes, t, &sh.ring[c][0][0][0], sh.P[c], T, lane, flush_every, stack_fill, stack_ovf, (stack_fill & 0x80000000u) ? status : nullptr);
             if (lane == 0) { sh.meta[slot].q = bad ? -1 - q : q; sh.meta[slot].tips = t; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.full[slot]);
@@ -908,7 +886,7 @@ static cudaError_t launch_resolve_mma_mix(const PlanDev &plan, const uint4 *plan
         }
     }
     kern<<<grid, kMmaWarps * 32, smem, stream>>>(plan, planes, ntips, quartets, m, seed, d_rscor, rstat, d_counts, d_minrank,
-                                                 d_status, flush_every, stack_fill_slots(), (uint32_t)g_stack_ovf.load(), 2u, d_skip);
+                                                 d_status, flush_every, stack_fill_slots(), (uint32_t)g_stack_ovf.load(), d_skip);
     ++g_launches;
     g_last_kernel = kSubsample ? "tq::resolve_mma_kernel<true>" : "tq::resolve_mma_kernel<false>";
     g_last_count_warps = NC;
