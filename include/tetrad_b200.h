@@ -239,7 +239,7 @@ int tq_pairgemm_stats(int64_t out[2]);
  *                      overflow rule "stack_ovf" alone decides), 0 = one product per tile (never stack), 1..99
  *   "stack_ovf"        a tile is stacked on the previous ones only if no lane has more than this many selected loci
  *                      whose bit slot is already taken (those are counted one by one, by shared-memory atomics);
- *                      otherwise the stack is multiplied out first.  0..32, default 7
+ *                      otherwise the stack is multiplied out first.  0..32, default 8
  *   "stack_stats"      != 0: the tensor-core kernel adds its stacking diagnostics to words 1..3 of the status block
  *                      (default 0: off)
  *   "count_warps"      count warps per CTA of the tensor-core kernel (of 16; the others score): 0 = chosen from the

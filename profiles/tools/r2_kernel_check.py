@@ -96,7 +96,7 @@ def mixes(config: str, mode: str, nq_cap: int = 1_000_000, reps: int = 3):
     fills = [int(x) for x in os.environ.get("TQ_FILLS", "-1").split(",")]
     ncs = [int(x) for x in os.environ.get("TQ_NCS", "0,8,12").split(",")]
     _lib.check(lib.tq_set_option(b"stack_stats", int(os.environ.get("TQ_STATS", "1"))))
-    ovfs = [int(x) for x in os.environ.get("TQ_OVFS", "7").split(",")]
+    ovfs = [int(x) for x in os.environ.get("TQ_OVFS", "8").split(",")]
     for nc, fill, ovf in [(a, b, c) for b in fills for c in ovfs for a in ncs]:
         _lib.check(lib.tq_set_option(b"count_warps", nc))
         _lib.check(lib.tq_set_option(b"stack_fill", fill))
@@ -120,7 +120,7 @@ def mixes(config: str, mode: str, nq_cap: int = 1_000_000, reps: int = 3):
               f"{len(q) / ms / 1e3:.3f} M quartets/s  same_results={chk == ref}  per quartet: products {per[0]:.1f} stacked {per[1]:.1f} walk {per[2]:.1f}", flush=True)
     _lib.check(lib.tq_set_option(b"count_warps", 0))
     _lib.check(lib.tq_set_option(b"stack_fill", -1))
-    _lib.check(lib.tq_set_option(b"stack_ovf", 7))
+    _lib.check(lib.tq_set_option(b"stack_ovf", 8))
 
 
 if __name__ == "__main__":

@@ -327,7 +327,7 @@ def test_stacked_tiles_count_every_locus_once(tb, oracle, count_warps):
         _lib.set_kernel("mma")
         _lib.check(lib.tq_set_option(b"count_warps", count_warps))
         _lib.check(lib.tq_set_option(b"stack_stats", 1))
-        for fill, ovf in ((0, 0), (85, 0), (-1, 7), (100, 32), (40, 3)):
+        for fill, ovf in ((0, 0), (85, 0), (-1, 8), (100, 32), (40, 3)):
             _lib.check(lib.tq_set_option(b"stack_fill", fill))
             _lib.check(lib.tq_set_option(b"stack_ovf", ovf))
             rstat, rscor, counts, minrank = eng.resolve(quartets, True, want_counts=True)
@@ -336,7 +336,7 @@ def test_stacked_tiles_count_every_locus_once(tb, oracle, count_warps):
             assert lib.tq_last_count_warps() == count_warps
     finally:
         _lib.set_kernel("auto")
-        for name, val in ((b"count_warps", 0), (b"stack_fill", -1), (b"stack_ovf", 7), (b"stack_stats", 0)):
+        for name, val in ((b"count_warps", 0), (b"stack_fill", -1), (b"stack_ovf", 8), (b"stack_stats", 0)):
             _lib.check(lib.tq_set_option(name, val))
     got = outs[0][2].view(np.uint32).reshape(-1, 16, 16)
     assert (got[::6] == det["mats"][:, 0]).all() and (outs[0][0].view(np.uint32)[::6] == ostat).all()

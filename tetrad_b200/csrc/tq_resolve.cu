@@ -73,7 +73,7 @@ std::atomic<int> g_stack_fill{initial_stack_fill()};     // < 0: default; else p
 static int initial_stack_ovf()
 {
     const char *e = getenv("TQ_STACK_OVF");
-    return e ? atoi(e) : 7;
+    return e ? atoi(e) : 8;
 }
 std::atomic<int> g_stack_ovf{initial_stack_ovf()};
 std::atomic<int> g_stack_stats{0};                       // != 0: the kernel adds its stacking diagnostics to status[1..3]       // most overflow loci a lane may have for a tile to be stacked
