@@ -1,11 +1,15 @@
 // Resolve kernels of the quartet-resolution hot path (sm_100a): fused count + score, only the result leaves the SM.
 //
-//   resolve_mma_kernel     the kernel large launches run.  8 count warps + 8 score warps per CTA, one CTA per SM.
-//                          Count warps: stage 1 selects one SNP per locus (running OR over the rank chunks of the four
-//                          tip rows), stage 2 forms the 256 site-pattern counts of every 1024-locus tile on the integer
-//                          tensor cores (IMMA.16832.U8.U8 on bit planes unpacked by one LOP3 per four loci); the tip rows
-//                          reach shared memory through a per-warp cp.async ring.  Score warps take four finished quartets
-//                          at a time through the FP64 QR + Jacobi of tq_svd.cuh.  (A CTA-wide ring of TMA bulk copies that
+//   resolve_mma_kernel     the kernel large launches run.  16 warps per CTA, one CTA per SM: 8 count + 8 score warps or
+//                          12 + 4, chosen from the plan (pick_count_warps).  Count warps: stage 1 selects one SNP per
+//                          locus (running OR over the rank chunks of the four tip rows; in subsample mode on
+//                          {hi, lo, valid} code planes converted per launch from the one-hot matrix: 18 LOP3 per chunk),
+//                          stacks the merged code planes of consecutive sparse tiles in registers (a locus whose bit
+//                          slot is taken is counted by a shared-memory atomic), and stage 2 forms the 256 site-pattern
+//                          counts of a stack of tiles on the integer tensor cores (IMMA.16832.U8.U8 on bit planes
+//                          unpacked by one LOP3 per four loci); the tip rows reach shared memory through a per-warp
+//                          cp.async ring.  Score warps take four finished quartets at a time through the FP64 QR +
+//                          Jacobi of tq_svd.cuh.  (A CTA-wide ring of TMA bulk copies that
 //                          holds every distinct row of eight consecutive quartets once was built and measured in round 2:
 //                          correct, but half as fast -- sharing one ring lock-steps the count warps, so their IMMA and load
 //                          phases stop overlapping, and four stages do not cover a bulk copy's latency;
@@ -16,9 +20,10 @@
 //   (full mode, dense quartet lists: tq_pairgemm.cu -- tcgen05.mma over tip pairs)
 //
 // launch_resolve picks by launch size; tq_set_option("kernel", ..) / TQ_KERNEL force one.  All give bit-identical results.
-// The measurements behind the constants (warp mix 8 + 8, ring depth 4, L1-bypassing cp.async, four mask scales, ...) are in
-// profiles/r01_v6_resolve_ncu.md and profiles/r01_v7_resolve_ncu.md; the build switches that produced them are in the
-// history of this file's predecessor (tq_kernels.cu, commit 425353e), not in the product.
+// The measurements behind the constants (warp mixes, ring depth 4, L1-bypassing cp.async, four mask scales, stack_ovf, ...)
+// are in profiles/r01_v6_resolve_ncu.md, profiles/r01_v7_resolve_ncu.md and profiles/r02_warp_mix.md; the build switches
+// that produced the round-1 ones are in the history of this file's predecessor (tq_kernels.cu, commit 425353e), not in
+// the product.
 //
 // Reference semantics restated here (paths relative to the reference repo):
 //   tetrad/src/resolve_quartets.py:212-221  gather, missing mask, invariant mask
