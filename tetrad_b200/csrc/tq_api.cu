@@ -216,11 +216,13 @@ static int build_plan(const std::vector<uint32_t> &run_start, const std::vector<
         DeviceGuard guard(device);
         pin = pinned_get(total + 4);
         if (!pin.ptr) return fail(TQ_ENOMEM, "tq_plan_create: no pinned host memory for the plan tables");
-        memset(pin.ptr, 0, (total + 4) * sizeof(uint32_t));
     } else {
-        vec.assign(total + 4, 0u);
+        vec.resize(total + 4);
     }
     uint32_t *tables = pin.ptr ? pin.ptr : vec.data();
+    // every word below is written by the loops that follow except the padding of the three per-locus tables and the tail
+    for (int64_t l = nloci; l < lpad; ++l) tables[o_start + l] = tables[o_len + l] = tables[o_run + l] = 0u;
+    for (size_t i = total; i < total + 4; ++i) tables[i] = 0u;
     for (int64_t r = 0; r < nloci; ++r) {
         const int64_t pos = bucket[max_len - run_len[r]]++;
         tables[o_start + pos] = run_start[r];
@@ -300,18 +302,27 @@ int tq_plan_create(const uint32_t *h_locus, int64_t ncols, int64_t stride, int d
     // locus runs (maximal runs of equal id, resolve_quartets.py:58-64)
     std::vector<uint32_t> run_start, run_len;
     bool monotone = true;
-    {
-        uint32_t prev = 0;
-        for (int64_t c = 0; c < ncols; ++c) {
+    if (ncols > 0) {
+        // one pass, run boundaries only (this loop is on the host entry's critical path: the pack waits for the plan)
+        // branch-free: a run boundary every few columns is a mispredicted branch every few columns otherwise (4.4 -> 1 ns
+        // per column)
+        run_start.resize((size_t)ncols + 1);
+        uint32_t *rs = run_start.data();
+        uint32_t prev = h_locus[0];
+        size_t n = 1;
+        rs[0] = 0u;
+        for (int64_t c = 1; c < ncols; ++c) {
             const uint32_t id = h_locus[c * stride];
-            if (c == 0 || id != prev) {
-                if (c > 0 && id < prev) monotone = false;
-                run_start.push_back((uint32_t)c);
-                run_len.push_back(0);
-            }
-            run_len.back()++;
+            rs[n] = (uint32_t)c;
+            n += id != prev;
+            monotone &= id >= prev;
             prev = id;
         }
+        run_start.resize(n);
+        const size_t nr = n;
+        run_len.resize(nr);
+        for (size_t r = 0; r + 1 < nr; ++r) run_len[r] = run_start[r + 1] - run_start[r];
+        run_len[nr - 1] = (uint32_t)ncols - run_start[nr - 1];
     }
     if (!monotone) {   // ids may come in any order, but every id must own exactly one run
         std::unordered_set<uint32_t> seen;
