@@ -273,7 +273,7 @@ def stacking_stats(lib, engine, run_once, nq):
             "overflow_walk_per_quartet": float(st[3]) / nq, "count_warps": int(lib.tq_last_count_warps()),
             "note": "subsample mode stacks the merged planes of consecutive sparse tiles before ONE 16 x 16 x 1024 tile product; "
                     "loci whose bit slot is taken are counted by shared-memory atomics (walk = the busiest lane's share); "
-                    "status words 1..3 of an extra untimed launch of the same shape (wrap at 2^32)"}
+                    "status words 1..3 of an extra untimed launch over at most 2^20 quartets of the same list"}
 
 
 def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local, subsample=True, kernel=None, stacking=None):
@@ -284,7 +284,7 @@ def roofline_block(config, ncols, quartets_per_launch, kern_ms, info, lib, local
     rec = ncu_record(config, subsample)
     ntiles, chunks = info["ntiles"], info["row_words"] / 128.0
     products = ntiles if subsample else chunks               # 16 x 16 x 1024 tile products per quartet
-    if subsample and stacking and stacking["tile_products_per_quartet"] < (1 << 32) / max(1, quartets_per_launch) * 0.9:
+    if subsample and stacking:
         products = stacking["tile_products_per_quartet"]     # stacked tiles: fewer products than tiles
     imma_per_quartet = 64.0 * products
     alu_per_quartet = 32.0 * (320.0 * products + (24.0 * chunks if subsample else 0.0))   # stage 1 on code planes: 18 LOP3 + loop arithmetic
@@ -397,7 +397,8 @@ def bench_static(config, world, rank, local, dev, lib, steps, warmup, subsample=
                quartets_per_launch=hi - lo, launches=int(launches), ncols=int(tmparr.shape[1]), info=dict(eng.info),
                tmparr=tmparr, tmpmap=tmpmap, quartets=quartets)
     if subsample:
-        res["stacking"] = stacking_stats(lib, eng, lambda: eng.resolve(qd[lo:hi], subsample), hi - lo)
+        ns = min(hi - lo, 1 << 20)                              # the u32 diagnostics would wrap on longer lists
+        res["stacking"] = stacking_stats(lib, eng, lambda: eng.resolve(qd[lo:lo + ns], subsample), ns)
     if e2e:
         # end to end through the reference-facing host API (pinned host buffers; plan + H2D + pack + resolve + D2H);
         # under N ranks every rank resolves its quartet range of the same matrix
@@ -475,7 +476,8 @@ def bench_replicates(config, world, rank, local, dev, lib, steps, warmup, sample
     kern_ms = statistics.mean(e["resolve_start"].elapsed_time(e["resolve_end"]) for e in ev)
     gather_ms = statistics.mean(e["resolve_end"].elapsed_time(e["gather_end"]) for e in ev)
     info = dict(preps[-1].engine.info)
-    stacking = stacking_stats(lib, preps[-1].engine, lambda: pipe.resolve(preps[-1]), -(-Q // world))
+    ns = min(-(-Q // world), 1 << 20)                           # the u32 diagnostics would wrap on longer lists
+    stacking = stacking_stats(lib, preps[-1].engine, lambda: preps[-1].engine.resolve(preps[-1].q_dev[:ns], True), ns)
     # ---- e2e: the same loop by wall clock, host draws + H2D + D2H of the results on rank 0 inside ----------------
     barrier(world, dev)
     t0 = time.perf_counter()
