@@ -159,3 +159,30 @@ def test_device_calls_fail_loudly_without_gpu(lib):
     rc, hp = _plan(lib, np.array([0, 0, 1], np.uint32))
     assert lib.tq_pack(hp, None, 4, 3, None, None) == _lib.TQ_EINVAL     # host-only plan
     lib.tq_plan_destroy(hp)
+
+
+@pytest.mark.parametrize("shuffle_ids", [False, True])
+def test_plan_tables_equal_a_numpy_restatement(lib, shuffle_ids):
+    """Every table of a plan against a numpy restatement on random run lengths (ids increasing, or any distinct ids):
+    stable sort by length (longest first), tiles of 1024 loci, K = the tile's longest locus, zero padding."""
+    rng = np.random.default_rng(11 + shuffle_ids)
+    nl = 2500
+    lens = rng.integers(1, 12, size=nl).astype(np.int64)
+    ids = rng.permutation(10 * nl)[:nl] if shuffle_ids else np.sort(rng.permutation(10 * nl)[:nl])
+    tmpmap = np.zeros((int(lens.sum()), 3), np.uint32)
+    tmpmap[:, 0] = np.repeat(ids, lens)
+    rc, h = _plan(lib, tmpmap, stride=3)
+    assert rc == 0
+    info, off, k, start, length = _tables(lib, h)
+    run = _tables.last_run
+    order = np.argsort(-lens, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    ntiles = (nl + 1023) // 1024
+    assert info[0] == lens.sum() and info[1] == nl and info[2] == ntiles and info[4] == lens.max()
+    assert (length[:nl] == lens[order]).all() and (start[:nl] == starts[order]).all() and (run[:nl] == order).all()
+    assert not length[nl:].any() and not start[nl:].any() and not run[nl:].any()                 # padding is zero
+    want_k = np.array([lens[order][t * 1024] for t in range(ntiles)])
+    assert (k == want_k).all() and (off == np.concatenate([[0], np.cumsum(want_k * 32)])).all()
+    assert info[3] == off[-1] * 4 and info[5] == (want_k * 1024).sum()
+    lib.tq_plan_destroy(h)
+
