@@ -142,7 +142,8 @@ int tq_boot_pack_rows(const tq_plan *plan, const uint8_t *d_seqarr, int64_t ntip
  * Outputs (device): d_rscor f64[m][3], d_rstat u32[m][2] = (best split, nsnps),
  *   d_counts u32[m][256] or NULL = mats[0] row-major (index 64a+16b+4c+d),
  *   d_minrank u32[m] or NULL.
- * subsample != 0 -> one SNP per locus (subsample_chunk_to_matrices); 0 -> all SNPs
+ * subsample != 0 -> one SNP per locus (subsample_chunk_to_matrices; a large launch first converts the packed matrix into
+ * {hi, lo, valid} words in stream-ordered scratch of the matrix's own size, freed behind the launch); 0 -> all SNPs
  * (full_chunk_to_matrices; chunks of the list whose quartets fill the tiles of a tip-pair grid densely -- exhaustive
  * lists and contiguous ranges of them -- go through one u8 GEMM over tip pairs on tcgen05.mma, decided on the device).  Tip indices must be < ntips (checked on the device: offending
  * quartets get best = 0xFFFFFFFF and word 0 of the call's status block, if given, is set non-zero).
